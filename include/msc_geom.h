@@ -1,0 +1,181 @@
+/*
+ * msc_geom.h -- C-ABI of the B200-native geometric-evidence path (libmsc_geom.so).
+ *
+ * The reference (AgustinRoca/multimodal-scene-captioning) has NO native/FFI interface: its boundary for
+ * this path is a set of Python callables.  This header is the C-ABI those
+ * callables bind to in the drop-in (ctypes); each entry point cites the reference
+ * function(s) it replaces.  All pointers are DEVICE pointers unless the name ends in _host; sizes are
+ * element counts; every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ * allocates or frees caller-visible memory, never throws, and returns 0 on success or a negative
+ * msc_status.  msc_last_error() returns a thread-local message for the last failure.
+ *
+ * Conventions: quaternions are [w,x,y,z]; a pose7 is (tx,ty,tz,qw,qx,qy,qz) f64; box sizes are (w,l,h)
+ * as in nuscenes_loader.py:184; raw sweep points are the .pcd.bin rows (x,y,z,intensity,ring) f32.
+ */
+#ifndef MSC_GEOM_H
+#define MSC_GEOM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSC_ABI_VERSION 1
+#define MSC_MAX_CAMS 8
+#define MSC_MAX_BOXES_FUSED 256 /* per sample, fused kernel (cull masks are ceil(B/32) words) */
+#define MSC_STATS_STRIDE 16
+
+typedef enum {
+    MSC_OK = 0,
+    MSC_ERR_BAD_ARGUMENT = -1,
+    MSC_ERR_LAUNCH = -2,
+    MSC_ERR_UNSUPPORTED = -3,
+    MSC_ERR_NO_DEVICE = -4
+} msc_status;
+
+/* Scalar parameters; names follow the reference's attributes where one exists. */
+typedef struct {
+    float remove_close_radius; /* devkit remove_close (App. A.1), 1.0                                     */
+    float range_min;           /* lidar_agent.py:107 `distances > 1.0`                                    */
+    float range_max;           /* lidar_agent.py:107 `distances < self.bev_range`                         */
+    float z_min;               /* lidar_agent.py:110 `pc[:,2] > -3.0`                                     */
+    float z_max;               /* lidar_agent.py:110 `pc[:,2] < 5.0`                                      */
+    float ground_z;            /* lidar_agent.py:115 ground_threshold = -1.4                              */
+    float bev_range;           /* lidar_agent.py:49  self.bev_range = 50                                  */
+    int32_t bev_res;           /* lidar_agent.py:48  self.bev_resolution (800) / 200 for the [EXT] grid   */
+    int32_t image_w;           /* 1600 */
+    int32_t image_h;           /* 900  */
+    int32_t n_cams;            /* 6, <= MSC_MAX_CAMS */
+    uint32_t fov_keep_mask;    /* 0: count per-camera wedge membership only; else keep points in any set camera */
+    int32_t centroid_shift;    /* fraction bits of the fixed-point centroid sums (20 for range_max <= 60)  */
+    int32_t intensity_shift;   /* fraction bits of the fixed-point intensity sums (8)                     */
+    /* square-root-free range thresholds on s = x*x + y*y (host: msc_geom.geometry.sqrt_thresholds) */
+    float s_lo;                /* smallest f32 s with sqrtf(s) > range_min */
+    float s_hi;                /* largest  f32 s with sqrtf(s) < range_max */
+} msc_params;
+
+/* A batch of samples laid out for the fused kernel.  Sweeps of all samples are concatenated; each sweep's
+ * first point must start at a multiple of 4 points (16-byte aligned rows for the bulk copies) and the
+ * points buffer must extend 16 bytes past the last sweep. */
+typedef struct {
+    int32_t n_samples;
+    int32_t max_boxes_per_sample;    /* max over samples of the box count (sizes the smem cull masks)     */
+    const float* points;             /* [n_points_padded, 5] raw sweep rows                               */
+    const int32_t* sample_sweep_off; /* [n_samples + 1] index into the sweep arrays                       */
+    const uint32_t* sweep_start;     /* [n_sweeps] first point of the sweep (multiple of 4)               */
+    const uint32_t* sweep_count;     /* [n_sweeps] points in the sweep                                    */
+    const double* sweep_pose;        /* [n_sweeps, 12] row-major 3x4 ref_from_sensor (App. A.1)           */
+    const int32_t* sample_box_off;   /* [n_samples + 1] index into boxes                                  */
+    const double* boxes;             /* [n_boxes, 10] global frame: center3, size(w,l,h), quat(w,x,y,z)   */
+    const double* ego_pose;          /* [n_samples, 7] ego pose at the LIDAR_TOP keyframe                 */
+    const double* lidar_calib;       /* [n_samples, 7] LIDAR_TOP calibrated sensor                        */
+    const double* cam_ego_pose;      /* [n_samples, n_cams, 7] ego pose at each camera's timestamp        */
+    const double* cam_calib;         /* [n_samples, n_cams, 7]                                            */
+    const double* cam_K;             /* [n_samples, n_cams, 9] row-major intrinsics                       */
+} msc_batch_in;
+
+/* Result tables.  bev_ci interleaves (count u32, intensity sum in Q<intensity_shift> u32) per cell so a
+ * cell is one 8-byte word for the out-of-window 64-bit reductions; the kernel zero-fills it itself. */
+typedef struct {
+    uint32_t* box_count;   /* [n_boxes]           points inside the box (devkit points_in_box, App. A.2)  */
+    float* box_nearest;    /* [n_boxes]           BEV distance of the nearest member point (+inf if none) */
+    float* box_centroid;   /* [n_boxes, 3]        centroid of member points (0 if none)                   */
+    uint8_t* proj_visible; /* [n_boxes, n_cams]   BoxVisibility.ANY flag (App. A.3)                       */
+    float* proj_extent;    /* [n_boxes, n_cams,4] umin,vmin,umax,vmax clipped to the image (0 if hidden)  */
+    uint32_t* bev_ci;      /* [n_samples, res, res, 2]                                                    */
+    float* bev_height;     /* [n_samples, res, res] running max of z, 0-initialised (lidar_agent.py:543,560) */
+    uint32_t* stats;       /* [n_samples, 16]: 0 n_in 1 n_after_close 2 n_kept 3 n_ground 4 n_object
+                                               5..12 per-camera wedge counts, 13 flags (bit0: a cell count
+                                               reached 65536, intensity sum may have wrapped)              */
+} msc_batch_out;
+
+int msc_abi_version(void);
+const char* msc_last_error(void);
+
+/* Device properties the host needs for launch configuration and reporting. */
+int msc_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor);
+
+/*
+ * The fused hot path: per-sweep rigid transform + remove_close + range/height filter + FOV wedges +
+ * ground/object split + oriented-box membership (count / nearest / centroid) + BEV occupancy/height/
+ * intensity grid + box->camera projection, one pass over the raw sweeps.
+ * Replaces: LiDARAgent._preprocess_point_cloud / _segment_ground (lidar_agent.py:103-132) and the raster
+ * half of _generate_multi_layer_bev (:539-560) for batches, plus the [EXT] rows e1-e5 of SURVEY.md
+ * section 8(a) (devkit from_file_multisweep, points_in_box, get_sample_data/view_points/box_in_image).
+ * workspace: >= msc_fused_workspace_bytes() bytes, 16-byte aligned (holds the work counter).
+ */
+size_t msc_fused_workspace_bytes(int32_t n_samples);
+int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
+ * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto),
+ * "cull_shift" (-1 auto).  get: also "last_window", "last_smem", "tile_pts", "stages", "threads". */
+int msc_fused_set_option(const char* key, int32_t value);
+int msc_fused_get_option(const char* key, int32_t* value);
+
+/*
+ * Materialised multi-sweep aggregation (devkit LidarPointCloud.from_file_multisweep, App. A.1) for one
+ * sample: order-preserving, writes rows (x',y',z',intensity) and the per-point time lag.
+ * n_out (device u32) receives the number of rows.  block_counts: scratch of ceil(n_sweeps_points/1024)+1 u32.
+ */
+int msc_aggregate_sweeps(float remove_close_radius, const float* points, int32_t n_sweeps,
+                         const uint32_t* sweep_start, const uint32_t* sweep_count, const double* sweep_pose,
+                         const float* sweep_time_lag, uint32_t max_points_per_sweep, float* out_xyzi, float* out_time,
+                         uint32_t* n_out, uint32_t* scratch, size_t scratch_elems, void* stream);
+
+/*
+ * Keyframe path, bit-exact drop-in for LiDARAgent._preprocess_point_cloud + _segment_ground
+ * (lidar_agent.py:103-132): order-preserving compaction of the kept rows into `kept` and of the ground /
+ * object subsets.  pts has `pitch` floats per row (4 mock loader, 5 devkit view, nuscenes_loader.py:152-155);
+ * outputs are dense (n,4).  counts (device u32[3]) = n_kept, n_ground, n_object.
+ */
+int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32_t n, int32_t pitch, float* kept,
+                              float* ground, float* object, uint32_t* counts, uint32_t* scratch, size_t scratch_elems,
+                              void* stream);
+
+/*
+ * Keyframe BEV raster layers, bit-exact for the pre-overlay half of LiDARAgent._generate_multi_layer_bev
+ * (lidar_agent.py:539-597): count u32, height f32 (0-initialised running max), semantic BGR u8 (ground
+ * colour, then object hot-colormap, last point in array order wins).  ground/object are dense (n,4).
+ * winner: scratch u32[res*res]; zrange: scratch u32[2].  Arrays are not flipped.
+ */
+int msc_keyframe_bev(const msc_params* params, const float* ground, uint32_t n_ground, const float* object,
+                     uint32_t n_object, uint32_t* count, float* height, uint8_t* semantic_bgr, uint32_t* winner,
+                     uint32_t* zrange, void* stream);
+
+/* Raw-cloud statistics (RawGPT4oBaseline._describe_point_cloud, baseline_gpt4o.py:276-285):
+ * out7 (device f64[7]) = min x,y,z, max x,y,z, sum of sqrt(x^2+y^2). */
+int msc_cloud_stats(const float* pts, uint32_t n, int32_t pitch, double* out7, void* stream);
+
+/* Per-annotation table (SceneGraphAgent._parse_annotations, scenegraph_agent.py:186-225; zones :281-295;
+ * RawGPT4oBaseline._describe_annotations region flags, baseline_gpt4o.py:304-317).  xy, vel: [n,2] f64.
+ * direction: 0 front 1 left 2 back 3 right; zone: 0..8 in the order of scenegraph_agent.py:136-146, 255 none;
+ * region_bits: bit0 x>0, bit1 y>0. */
+int msc_annotation_table(int32_t n, const double* xy, const double* vel, double* distance, uint8_t* direction,
+                         uint8_t* moving, uint8_t* zone, uint8_t* region_bits, void* stream);
+
+/* Box footprints for the relation table: rect [n,6] f64 = x, y, ux, uy, half_len, half_wid in the ego frame
+ * of ego_pose (NULL: stay in the loader's global frame). */
+int msc_box_footprints(int32_t n, const double* boxes, const double* ego_pose, double* rect, void* stream);
+
+/* [EXT] pairwise relation table for n annotations: dist/bearing f32 [n,n], category/overlap u8 [n,n]. */
+int msc_relation_table(int32_t n, const double* rect, float* dist, float* bearing, uint8_t* category,
+                       uint8_t* overlap, void* stream);
+
+/* [EXT] standalone box -> camera projection (also fused into msc_fused_evidence_batch). */
+int msc_project_boxes(int32_t n_boxes, const double* boxes, int32_t n_cams, const double* cam_ego_pose,
+                      const double* cam_calib, const double* cam_K, int32_t image_w, int32_t image_h,
+                      uint8_t* visible, float* extent, void* stream);
+
+/* Per-cluster axis-aligned metadata (lidar_agent.py:200-204): out [n_clusters, 11] f32 =
+ * min3, max3, center3, distance, num_points.  labels: i32 per row of pts (-1 = noise). */
+int msc_cluster_aabb(const float* pts, uint32_t n, int32_t pitch, const int32_t* labels, int32_t n_clusters,
+                     float* out11, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSC_GEOM_H */

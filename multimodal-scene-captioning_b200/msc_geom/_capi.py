@@ -1,0 +1,110 @@
+"""ctypes binding of libmsc_geom.so (C-ABI in include/msc_geom.h).  No CPU fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libmsc_geom.so")
+
+MSC_MAX_CAMS = 8
+MSC_MAX_BOXES_FUSED = 256
+MSC_STATS_STRIDE = 16
+ABI_VERSION = 1
+
+
+class MscError(RuntimeError):
+    pass
+
+
+class MscParams(C.Structure):
+    _fields_ = [
+        ("remove_close_radius", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float), ("z_min", C.c_float),
+        ("z_max", C.c_float), ("ground_z", C.c_float), ("bev_range", C.c_float), ("bev_res", C.c_int32),
+        ("image_w", C.c_int32), ("image_h", C.c_int32), ("n_cams", C.c_int32), ("fov_keep_mask", C.c_uint32),
+        ("centroid_shift", C.c_int32), ("intensity_shift", C.c_int32), ("s_lo", C.c_float), ("s_hi", C.c_float),
+    ]
+
+
+class MscBatchIn(C.Structure):
+    _fields_ = [
+        ("n_samples", C.c_int32), ("max_boxes_per_sample", C.c_int32), ("points", C.c_void_p),
+        ("sample_sweep_off", C.c_void_p), ("sweep_start", C.c_void_p), ("sweep_count", C.c_void_p),
+        ("sweep_pose", C.c_void_p), ("sample_box_off", C.c_void_p), ("boxes", C.c_void_p), ("ego_pose", C.c_void_p),
+        ("lidar_calib", C.c_void_p), ("cam_ego_pose", C.c_void_p), ("cam_calib", C.c_void_p), ("cam_K", C.c_void_p),
+    ]
+
+
+class MscBatchOut(C.Structure):
+    _fields_ = [
+        ("box_count", C.c_void_p), ("box_nearest", C.c_void_p), ("box_centroid", C.c_void_p), ("proj_visible", C.c_void_p),
+        ("proj_extent", C.c_void_p), ("bev_ci", C.c_void_p), ("bev_height", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+_lib = None
+
+_PROTOS = {
+    "msc_abi_version": (C.c_int, []),
+    "msc_last_error": (C.c_char_p, []),
+    "msc_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 4),
+    "msc_fused_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "msc_fused_evidence_batch": (C.c_int, [C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
+    "msc_fused_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "msc_fused_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
+    "msc_aggregate_sweeps": (C.c_int, [C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msc_keyframe_filter_split": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msc_keyframe_bev": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msc_cloud_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "msc_annotation_table": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "msc_box_footprints": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msc_relation_table": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msc_project_boxes": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msc_cluster_aabb": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load libmsc_geom.so; raises MscError when it has not been built (there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise MscError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(make -C multimodal-scene-captioning_b200/csrc). There is no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError here means the library and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.msc_abi_version() != ABI_VERSION:
+        raise MscError(f"ABI mismatch: library {lib.msc_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().msc_last_error().decode("utf-8", "replace")
+        raise MscError(f"{what} failed with status {status}: {msg}")
+
+
+def set_option(key: str, value: int):
+    check(load().msc_fused_set_option(key.encode(), int(value)), f"set_option({key})")
+
+
+def get_option(key: str) -> int:
+    v = C.c_int32(0)
+    check(load().msc_fused_get_option(key.encode(), C.byref(v)), f"get_option({key})")
+    return int(v.value)

@@ -1,0 +1,152 @@
+"""GeometryEngine -- host driver of the CUDA path.  PyTorch only owns device memory and streams; every
+computation goes through the C-ABI (include/msc_geom.h).  There is no CPU fallback anywhere in this file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import MscBatchIn, MscBatchOut, MscParams
+from .layout import GeomParams, HostBatch, pack_batch
+
+_IN_FIELDS = ("points", "sample_sweep_off", "sweep_start", "sweep_count", "sweep_pose", "sample_box_off", "boxes", "ego_pose",
+              "lidar_calib", "cam_ego_pose", "cam_calib", "cam_K")
+
+_NP2TORCH = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32,
+             np.dtype(np.uint32): torch.int32, np.dtype(np.uint8): torch.uint8}
+
+
+def _as_torch_cpu(a: np.ndarray) -> torch.Tensor:
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(a)
+
+
+def make_params(p: GeomParams) -> MscParams:
+    s_lo, s_hi = p.thresholds()
+    return MscParams(p.remove_close_radius, p.range_min, p.range_max, p.z_min, p.z_max, p.ground_z, p.bev_range, p.bev_res, p.image_w,
+                     p.image_h, p.n_cams, p.fov_keep_mask, p.centroid_shift, p.intensity_shift, s_lo, s_hi)
+
+
+@dataclass
+class DeviceBatch:
+    """A HostBatch resident in HBM."""
+    host: HostBatch
+    tensors: Dict[str, torch.Tensor]
+
+    def struct(self) -> MscBatchIn:
+        t = self.tensors
+        return MscBatchIn(self.host.n_samples, self.host.max_boxes_per_sample, *[t[k].data_ptr() for k in _IN_FIELDS])
+
+
+@dataclass
+class BatchResult:
+    """Result tables of msc_fused_evidence_batch, still on the device."""
+    n_samples: int
+    n_cams: int
+    res: int
+    intensity_shift: int
+    sample_box_off: np.ndarray
+    box_count: torch.Tensor
+    box_nearest: torch.Tensor
+    box_centroid: torch.Tensor
+    proj_visible: torch.Tensor
+    proj_extent: torch.Tensor
+    bev_ci: torch.Tensor
+    bev_height: torch.Tensor
+    stats: torch.Tensor
+
+    def struct(self) -> MscBatchOut:
+        return MscBatchOut(self.box_count.data_ptr(), self.box_nearest.data_ptr(), self.box_centroid.data_ptr(),
+                           self.proj_visible.data_ptr(), self.proj_extent.data_ptr(), self.bev_ci.data_ptr(), self.bev_height.data_ptr(),
+                           self.stats.data_ptr())
+
+    def table_tensors(self):
+        """Small per-box / per-sample tables (what NCCL gathers; BEV grids stay sharded)."""
+        return [self.box_count, self.box_nearest, self.box_centroid, self.proj_visible, self.proj_extent, self.stats]
+
+    def to_host(self, with_bev: bool = True) -> Dict[str, np.ndarray]:
+        out = {
+            "box_count": self.box_count.cpu().numpy().view(np.uint32),
+            "box_nearest": self.box_nearest.cpu().numpy(),
+            "box_centroid": self.box_centroid.cpu().numpy(),
+            "proj_visible": self.proj_visible.cpu().numpy(),
+            "proj_extent": self.proj_extent.cpu().numpy(),
+            "stats": self.stats.cpu().numpy().view(np.uint32),
+            "sample_box_off": self.sample_box_off,
+        }
+        if with_bev:
+            ci = self.bev_ci.cpu().numpy().view(np.uint32)
+            out["bev_count"] = np.ascontiguousarray(ci[..., 0])
+            out["bev_isum_q"] = np.ascontiguousarray(ci[..., 1])
+            out["bev_intensity_sum"] = (ci[..., 1].astype(np.float64) / float(1 << self.intensity_shift)).astype(np.float32)
+            out["bev_height"] = self.bev_height.cpu().numpy()
+        return out
+
+
+class GeometryEngine:
+    """Owns the device, the loaded library and reusable output buffers."""
+
+    def __init__(self, device: Optional[int] = None, params: Optional[GeomParams] = None):
+        if not torch.cuda.is_available():
+            raise _capi.MscError("GeometryEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _capi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        self.params = params or GeomParams()
+        sm, smem, maj, mnr = (C.c_int32() for _ in range(4))
+        _capi.check(self.lib.msc_device_info(C.byref(sm), C.byref(smem), C.byref(maj), C.byref(mnr)), "msc_device_info")
+        self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, (maj.value, mnr.value)
+        self._workspace = torch.zeros(64, dtype=torch.int32, device=self.device)
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ transfers
+    def upload(self, hb: HostBatch, pinned: Optional[Dict[str, torch.Tensor]] = None, non_blocking: bool = False) -> DeviceBatch:
+        tensors = {}
+        for k in _IN_FIELDS:
+            src = pinned[k] if pinned is not None else _as_torch_cpu(getattr(hb, k))
+            tensors[k] = src.to(self.device, non_blocking=non_blocking)
+        return DeviceBatch(hb, tensors)
+
+    @staticmethod
+    def pin(hb: HostBatch) -> Dict[str, torch.Tensor]:
+        return {k: _as_torch_cpu(getattr(hb, k)).pin_memory() for k in _IN_FIELDS}
+
+    def alloc_result(self, hb: HostBatch, params: Optional[GeomParams] = None) -> BatchResult:
+        p = params or self.params
+        S, B, Cn, R = hb.n_samples, hb.n_boxes, p.n_cams, p.bev_res
+        d = self.device
+        return BatchResult(
+            S, Cn, R, p.intensity_shift, hb.sample_box_off.copy(),
+            torch.empty(B, dtype=torch.int32, device=d), torch.empty(B, dtype=torch.float32, device=d),
+            torch.empty((B, 3), dtype=torch.float32, device=d), torch.empty((B, Cn), dtype=torch.uint8, device=d),
+            torch.empty((B, Cn, 4), dtype=torch.float32, device=d), torch.empty((S, R, R, 2), dtype=torch.int32, device=d),
+            torch.empty((S, R, R), dtype=torch.float32, device=d), torch.empty((S, _capi.MSC_STATS_STRIDE), dtype=torch.int32, device=d))
+
+    # ------------------------------------------------------------------ the hot path
+    def run_fused(self, db: DeviceBatch, out: Optional[BatchResult] = None, params: Optional[GeomParams] = None) -> BatchResult:
+        p = params or self.params
+        if p.n_cams != db.host.n_cams:
+            raise _capi.MscError(f"params.n_cams={p.n_cams} but the batch was packed for {db.host.n_cams} cameras")
+        if out is None:
+            out = self.alloc_result(db.host, p)
+        mp, bi, bo = make_params(p), db.struct(), out.struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), self._workspace.data_ptr(),
+                                                      self._workspace.numel() * 4, C.c_void_p(stream)), "msc_fused_evidence_batch")
+        self.kernel_launches += 1
+        return out
+
+    def process_samples(self, samples: Sequence[dict], params: Optional[GeomParams] = None) -> Dict[str, np.ndarray]:
+        """Host-in / host-out convenience: pack, upload, run, download."""
+        p = params or self.params
+        hb = pack_batch(list(samples), n_cams=p.n_cams)
+        res = self.run_fused(self.upload(hb), params=p)
+        torch.cuda.synchronize(self.device)
+        return res.to_host()
