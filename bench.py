@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- LiDAR samples/sec of the fused geometric-evidence path (10-sweep, in-box + BEV + proj).
+
+One "step" = one pass of the hot path over one batch of synthetic nuScenes-shaped samples
+(BASELINE.json configs[2] shape: 10 sweeps x 34,720 points, 60 boxes, 6 cameras, 200x200 BEV at 0.5 m).
+Weak scaling: every rank processes `--samples-per-gpu` samples; `value` is the whole-job aggregate.
+
+    python bench.py [--gpus N --steps K --warmup W]          (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU oracle port on the host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-scene-captioning_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "lidar_samples_per_sec_10sweep_inbox_bev_proj"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=592, help="batch per rank (4 per SM); inputs ~4.1 GB >> L2")
+    ap.add_argument("--unique", type=int, default=37, help="distinct synthetic samples generated per rank, tiled to the batch")
+    ap.add_argument("--workload", default="config3", choices=["config3", "config2", "mini"],
+                    help="config3: 10 sweeps, 60 boxes; config2: single keyframe; mini: 10 sweeps, 60-120 boxes")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fov", type=int, default=1)
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--config", type=int, default=0, help="launch shape of the fused kernel (see msc_fused_set_option)")
+    ap.add_argument("--cull-shift", type=int, default=-1)
+    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: knock out stages of the fused kernel (results invalid)")
+    ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")
+    return ap.parse_args()
+
+
+def workload_kwargs(name):
+    if name == "config2":
+        return dict(n_sweeps=1, n_boxes=60), "config2: 1 keyframe x 34,720 pts, 60 boxes, 6 cams, BEV 200x200"
+    if name == "mini":
+        return dict(n_sweeps=10, n_boxes="mini"), "config4-shape: 10 sweeps x 34,720 pts, 60-120 boxes, 6 cams, BEV 200x200"
+    return dict(n_sweeps=10, n_boxes=60), "config3: 10 sweeps x 34,720 pts (347,200), 60 boxes, 6 cams, BEV 200x200 @0.5m"
+
+
+def algorithmic_bytes(hb, params) -> int:
+    """bytes the path must move once -- raw rows in, result tables out."""
+    G = params.bev_res * params.bev_res
+    C = params.n_cams
+    n_sweeps = int(hb.sweep_count.shape[0])
+    return int(20 * hb.n_points + 96 * n_sweeps + (80 + 20 + 17 * C) * hb.n_boxes + hb.n_samples * (12 * G + 64 + 56 * 2 + C * (56 * 2 + 72)))
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_oracle_throughput(hb, params, n_samples: int, threads: int):
+    """Time the scalar oracle (tests/oracle_bridge.py -> oracle/libmsc_oracle.so) on the host cores.
+    ctypes releases the GIL, so a thread pool uses `threads` cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests.oracle_bridge import oracle_fused
+    idx = [i % hb.n_samples for i in range(n_samples)]
+    oracle_fused(hb, 0, params)  # warm-up (page-in, lazy build)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: oracle_fused(hb, i, params), idx))
+    dt = time.perf_counter() - t0
+    return n_samples / dt, dt
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from msc_geom.layout import GeomParams, pack_batch, tile_batch
+    from msc_geom.synthetic import make_sample
+
+    params = GeomParams()
+    wkw, wname = workload_kwargs(args.workload)
+    cores = os.cpu_count() or 1
+
+    # ---------------------------------------------------------------- reference arm: CPU oracle port, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_unique = min(args.unique, 8)
+        hb = pack_batch([make_sample(i, **wkw) for i in range(n_unique)])
+        per_step = args.cpu_samples or max(cores, 8)
+        for _ in range(max(args.warmup, 1) if args.warmup else 0):
+            cpu_oracle_throughput(hb, params, max(cores, 2), cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_oracle_throughput(hb, params, per_step, cores)
+        dt = time.perf_counter() - t0
+        val = args.steps * per_step / dt
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": wname, "samples_per_step": per_step},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{per_step} samples per step x {args.steps} steps, scalar C oracle, {cores} threads"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    from msc_geom import _capi
+    from msc_geom.engine import GeometryEngine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = GeometryEngine(local_rank, params)
+    _capi.set_option("fov", args.fov)
+    _capi.set_option("window", args.window)
+    _capi.set_option("config", args.config)
+    _capi.set_option("cull_shift", args.cull_shift)
+    _capi.set_option("debug_skip", args.debug_skip)
+
+    S = args.samples_per_gpu
+    n_unique = max(1, min(args.unique, S))
+    reps = (S + n_unique - 1) // n_unique
+    base = rank * 100000
+    hb_u = pack_batch([make_sample(base + i, **wkw) for i in range(n_unique)])
+    hb = tile_batch(hb_u, reps)
+    S = hb.n_samples
+    db = eng.upload(hb)
+    out = eng.alloc_result(hb)
+    abytes = algorithmic_bytes(hb, params)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = None
+    if world > 1:
+        tabs = out.table_tensors()
+        gathered = [torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in tabs]
+
+    def step():
+        eng.run_fused(db, out)
+        if world > 1:  # NCCL only gathers the small result tables; BEV grids stay sharded
+            for t, g in zip(out.table_tensors(), gathered):
+                dist.all_gather_into_tensor(g, t)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.kernel_launches
+    kern_events = []
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ka.record(stream)
+        eng.run_fused(db, out)
+        kb.record(stream)
+        kern_events.append((ka, kb))
+        if world > 1:
+            for t, g in zip(out.table_tensors(), gathered):
+                dist.all_gather_into_tensor(g, t)
+    e1.record(stream)
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in kern_events]
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * S * args.steps / (elapsed_ms * 1e-3)
+    gpu_launches = eng.kernel_launches - launches0
+    kavg_ms = sum(kern_ms) / len(kern_ms)
+
+    # ---------------------------------------------------------------- end to end: pinned host buffers in, host tables out
+    e2e = None
+    if not args.no_e2e:
+        # one chunk = one copy of the distinct-sample set (loader-format flat buffers) in pinned host memory;
+        # three staging slots / streams so H2D, kernel and D2H of neighbouring chunks overlap
+        n_slots = 3
+        pinned = [eng.pin(hb_u) for _ in range(n_slots)]
+        streams = [torch.cuda.Stream() for _ in range(n_slots)]
+        outs = [eng.alloc_result(hb_u) for _ in range(n_slots)]
+        host_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (o.table_tensors() + [o.bev_ci, o.bev_height])]
+                    for o in outs]
+        h2d = sum(int(t.numel() * t.element_size()) for t in pinned[0].values()) * reps
+        d2h = sum(int(t.numel() * t.element_size()) for t in host_out[0]) * reps
+
+        def e2e_step():
+            for ci in range(reps):
+                slot = ci % n_slots
+                with torch.cuda.stream(streams[slot]):
+                    dbc = eng.upload(hb_u, pinned=pinned[slot], non_blocking=True)
+                    eng.run_fused(dbc, outs[slot])
+                    for src, dst in zip(outs[slot].table_tensors() + [outs[slot].bev_ci, outs[slot].bev_height], host_out[slot]):
+                        dst.copy_(src, non_blocking=True)
+            for s in streams:
+                s.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        n_e2e = reps * hb_u.n_samples
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n_e2e * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------------------------------------------------------- roofline + CPU baseline (rank 0)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = abytes / (kavg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "fused_evidence_kernel", "kernel_ms": kavg_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        n_cpu = args.cpu_samples or 4 * cores
+        v, dt = cpu_oracle_throughput(hb_u, params, n_cpu, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} samples of the same workload, scalar C oracle (oracle/c/msc_oracle.c), {cores} threads, {dt:.1f} s wall"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": f"synthetic ({n_unique} distinct seeded samples per rank tiled x{reps}, distinct memory)",
+            "config": {"workload": wname, "samples_per_gpu": S, "points_per_step_per_gpu": hb.n_points,
+                       "l2_policy": "inputs (%.2f GB per step) larger than L2; no explicit flush" % (hb.points.nbytes / 1e9),
+                       "fov_counts": bool(args.fov), "bev_window_cells": _capi.get_option("last_window"),
+                       "tile_pts": _capi.get_option("tile_pts"), "stages": _capi.get_option("stages"),
+                       "threads": _capi.get_option("threads")},
+            "e2e": e2e, "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -24,7 +24,7 @@ extern "C" {
 
 #define MSC_ABI_VERSION 1
 #define MSC_MAX_CAMS 8
-#define MSC_MAX_BOXES_FUSED 256 /* per sample, fused kernel (cull masks are ceil(B/32) words) */
+#define MSC_MAX_BOXES_FUSED 255 /* per sample, fused kernel (cull cells hold u8 box ids; 0xff = empty) */
 #define MSC_STATS_STRIDE 16
 
 typedef enum {
@@ -111,7 +111,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
- * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto),
+ * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv",
  * "cull_shift" (-1 auto).  get: also "last_window", "last_smem", "tile_pts", "stages", "threads". */
 int msc_fused_set_option(const char* key, int32_t value);
 int msc_fused_get_option(const char* key, int32_t* value);

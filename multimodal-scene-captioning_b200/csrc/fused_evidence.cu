@@ -9,41 +9,53 @@
 //
 // B200 mapping:
 //   * persistent grid, one CTA per SM, one sample per CTA at a time (dynamic work counter);
-//   * raw sweep rows stream HBM -> smem through a 4-stage ring of 20 KB cp.async.bulk (TMA) tiles with
-//     mbarrier completion and an L2 evict-first policy; threads read x,y,z,i at a 5-word stride, which
-//     is bank-conflict free (5 is odd);
+//   * raw sweep rows stream HBM -> smem through a ring of 20 KB cp.async.bulk (TMA) tiles with mbarrier
+//     completion and an L2 evict-first policy; threads read x,y,z,i at a 5-word stride, which is
+//     bank-conflict free (5 is odd);
 //   * the BEV accumulators of a centred window of the grid live in smem as (count u32, isum u32) pairs
 //     updated with native integer ATOMS; cells outside the window take ONE 64-bit RED on the interleaved
 //     global cell; the window is flushed once per sample with coalesced 16-byte stores;
-//   * box tables, cull bitmasks and per-box accumulators are smem-resident; centroid sums are 64-bit
-//     fixed point (two 32-bit ATOMS with carry) so results are order-independent and bit-reproducible;
+//   * one 8-byte smem entry per 2 m cull cell carries up to four candidate box ids (oriented, conservative
+//     rasterisation) and the per-camera wedge classification (inside / straddling), so a point costs one
+//     LDS.64 to learn which boxes and which exact wedge tests it needs;
+//   * per-box accumulators are smem-resident integers: count, min s, and centroid sums split into three
+//     9-bit limbs per axis so every update is a fire-and-forget ATOMS (order-independent, bit-reproducible);
 //   * no tensor cores: nothing here is a contraction.
 #include "msc_common.cuh"
 
 namespace msc {
 
-#ifndef MSC_TILE_PTS
-#define MSC_TILE_PTS 1024
-#endif
-#ifndef MSC_STAGES
-#define MSC_STAGES 4
-#endif
-#ifndef MSC_THREADS
-#define MSC_THREADS 512
-#endif
-constexpr int kTilePts = MSC_TILE_PTS;
-constexpr int kStages = MSC_STAGES;
-constexpr int kThreads = MSC_THREADS;
-constexpr int kTileBytes = kTilePts * 20;
-constexpr int kPtsPerThread = kTilePts / kThreads;
-static_assert(kTilePts % kThreads == 0, "tile must be a multiple of the CTA size");
-static_assert(kTileBytes % 128 == 0, "tile stride keeps 128-byte alignment");
+// Launch shape: NT consumer threads + one producer warp.  A tile is NT*PPT points (20 B each).
+template <int NT, int PPT, int STAGES>
+struct Cfg {
+    static constexpr int kThreads = NT;            // consumer threads
+    static constexpr int kBlock = NT + 128;        // + one producer warpgroup (only its first warp issues TMA)
+    // setmaxnreg budgets: the producer warpgroup shrinks to 24 registers, the consumers take what that frees
+    static constexpr int kRegsLaunch = ((65536 / kBlock) / 8) * 8;
+    static constexpr int kRegsProducer = 24;
+    // consumers only take what the producer warpgroup released (never more: setmaxnreg.inc would spin forever)
+    static constexpr int kRegsConsumerRaw = kRegsLaunch + ((128 * (kRegsLaunch - kRegsProducer)) / NT / 8) * 8;
+    static constexpr int kRegsConsumer = kRegsConsumerRaw > 232 ? 232 : kRegsConsumerRaw;
+    static constexpr int kPtsPerThread = PPT;
+    static constexpr int kTilePts = NT * PPT;
+    static constexpr int kTileBytes = kTilePts * 20;
+    static constexpr int kStages = STAGES;
+    static constexpr int kWarps = NT / 32;
+    static_assert(kTileBytes % 128 == 0, "tile stride keeps 128-byte alignment");
+    static_assert(STAGES <= 8, "Misc holds 8 barriers per kind");
+};
+constexpr int kMaxSweepsSmem = 64;  // per-sample sweep table cached in smem (larger samples read it from global)
+constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes the four LDS.128 conflict-free
+
+constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
+constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
+constexpr int kAccWords = 12;                 // per-box accumulators: count, min s, 3 x 3 limbs, pad
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
-    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, misc_off, total_bytes;
-    int32_t win_w, win_lo;        // window covers cells [win_lo, win_lo + win_w) in x and y
-    int32_t cull_dim, cull_shift; // cull cell = BEV cell >> cull_shift
-    int32_t max_boxes;            // capacity of the smem box tables
+    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, lut_off, misc_off, total_bytes;
+    int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
+    int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
+    int32_t max_boxes;             // capacity of the smem box tables
 };
 
 struct FusedArgs {
@@ -52,194 +64,321 @@ struct FusedArgs {
     msc_batch_out out;
     FusedLayout L;
     uint32_t* work_counter;
+    // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
+    float two_r, resf, rcp_two_r, cscale, iscale;
+    int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
+    uint32_t debug_skip;    // profiling only (option "debug_skip"): 1 global atomics, 2 box loop, 4 window atomics, 8 box accumulate
 };
 
 struct Misc {  // small per-CTA state at misc_off
-    uint64_t full_bar[8];
+    uint64_t full_bar[8];   // TMA bytes landed (producer -> consumers)
+    uint64_t empty_bar[8];  // every consumer warp is done with the stage (consumers -> producer)
     float wedge[MSC_MAX_CAMS][6];
     uint32_t stats[MSC_STATS_STRIDE];
+    uint32_t sweep_start[kMaxSweepsSmem], sweep_count[kMaxSweepsSmem];
     int32_t sample;
 };
 
-// 64-bit two's-complement accumulate built from two native 32-bit shared atomics
-__device__ __forceinline__ void smem_add_s64(uint32_t* lo_hi, int32_t q) {
-    uint32_t ql = (uint32_t)q;
-    uint32_t old = atomicAdd(lo_hi, ql);
-    int32_t hi_delta = (int32_t)((uint32_t)(old + ql) < ql) - (int32_t)(q < 0);
-    if (hi_delta != 0) atomicAdd(lo_hi + 1, (uint32_t)hi_delta);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int R>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+// volatile so the compiler can neither rematerialise nor re-issue the load: the pose stays in registers
+__device__ __forceinline__ void ld_pose(const double* __restrict__ p, double M[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i += 2)
+        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(M[i]), "=d"(M[i + 1]) : "l"(p + i));
+}
+template <int N>
+__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the NT consumer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
 }
 
-template <int MASK_WORDS, bool FOV>
-__global__ void __launch_bounds__(kThreads, 1) fused_evidence_kernel(const __grid_constant__ FusedArgs A) {
+// BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
+// sequence, which tools/markstein_check.c proves equal to RN(a/b) for every float a outside the subnormal
+// quotient range for the whitelisted divisors (a = fl(c + r) is 0 or >= 2^-24 r here).
+template <bool FASTDIV>
+__device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp_two_r, float resf, int res_m1) {
+    const float a = __fadd_rn(c, r);
+    float q;
+    if (FASTDIV) {
+        const float q0 = __fmul_rn(a, rcp_two_r);
+        const float rem = __fmaf_rn(-two_r, q0, a);
+        q = __fmaf_rn(rem, rcp_two_r, q0);
+    } else {
+        q = __fdiv_rn(a, two_r);
+    }
+    const int i = __float2int_rz(__fmul_rn(q, resf));
+    return min(max(i, 0), res_m1);
+}
+
+// ------------------------------------------------------------------------------------------------ prologue
+// box preparation (global -> ego -> sensor, devkit points_in_box vectors, App. A.2) + cull rasterisation
+__device__ __noinline__ void prepare_box(const FusedArgs& A, const double* __restrict__ box, const double* __restrict__ ego,
+                                         const double* __restrict__ lcal, int b, float* __restrict__ boxp, uint2* __restrict__ cull) {
+    const msc_params& P = A.P;
+    const FusedLayout& L = A.L;
+    double c[3] = {box[0], box[1], box[2]};
+    double R[9];
+    quat_to_rot(box + 6, R);
+    frame_change(ego, c, R);
+    frame_change(lcal, c, R);
+    const double w = box[3], l = box[4], h = box[5];
+    const double hl = l / 2.0, hw = w / 2.0, hh = h / 2.0;
+    float* o = boxp + b * kBoxStride;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        o[r] = (float)(((R[r * 3 + 0] * hl + R[r * 3 + 1] * hw) + R[r * 3 + 2] * hh) + c[r]);
+        o[3 + r] = (float)(-(l * R[r * 3 + 0]));
+        o[6 + r] = (float)(-(w * R[r * 3 + 1]));
+        o[9 + r] = (float)(-(h * R[r * 3 + 2]));
+    }
+    o[12] = __fmaf_rn(o[5], o[5], __fmaf_rn(o[4], o[4], __fmul_rn(o[3], o[3])));
+    o[13] = __fmaf_rn(o[8], o[8], __fmaf_rn(o[7], o[7], __fmul_rn(o[6], o[6])));
+    o[14] = __fmaf_rn(o[11], o[11], __fmaf_rn(o[10], o[10], __fmul_rn(o[9], o[9])));
+    o[15] = 0.0f;
+    // Conservative oriented rasterisation of the xy footprint (a zonotope spanned by the projected edge
+    // vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the
+    // 2 mm margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
+    const float margin = 2e-3f;
+    const float cx = (float)c[0], cy = (float)c[1];
+    const float ex[3] = {o[3], o[6], o[9]}, ey[3] = {o[4], o[7], o[10]};
+    const float rx = 0.5f * (fabsf(ex[0]) + fabsf(ex[1]) + fabsf(ex[2])) + margin;
+    const float ry = 0.5f * (fabsf(ey[0]) + fabsf(ey[1]) + fabsf(ey[2])) + margin;
+    const int res_m1 = P.bev_res - 1;
+    const int cx0 = bev_cell<false>(cx - rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cx1 = bev_cell<false>(cx + rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy0 = bev_cell<false>(cy - ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
+    const int last = L.cull_dim - 1;
+    for (int gy = cy0; gy <= cy1; ++gy) {
+        for (int gx = cx0; gx <= cx1; ++gx) {
+            // cell rectangle in metres (edge cells absorb everything clipped into them: treat them as unbounded
+            // by skipping the separating-axis rejection there)
+            bool reject = false;
+            if (gx > 0 && gx < last && gy > 0 && gy < last) {
+                const float mx = -P.bev_range + ((float)gx + 0.5f) * cell_m, my = -P.bev_range + ((float)gy + 0.5f) * cell_m;
+                const float dx = cx - mx, dy = cy - my;
+                const float hc = 0.5f * cell_m + margin;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    // axis = normal of projected edge k
+                    const float nx = -ey[k], ny = ex[k];
+                    const float nn = fabsf(nx) + fabsf(ny);
+                    if (nn > 1e-6f) {
+                        const float dist = fabsf(dx * nx + dy * ny);
+                        float rb = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) rb += 0.5f * fabsf(ex[j] * nx + ey[j] * ny);
+                        const float rc = hc * nn;
+                        if (dist > (rb + rc) * 1.0001f + margin * nn) reject = true;
+                    }
+                }
+            }
+            if (reject) continue;
+            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
+            for (;;) {
+                const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
+                if (old == kCullAll) break;
+                uint32_t nw = kCullAll;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (nw == kCullAll && ((old >> (8 * k)) & 0xffu) == 0xffu) nw = (old & ~(0xffu << (8 * k))) | ((uint32_t)b << (8 * k));
+                if (atomicCAS(slot, old, nw) == old) break;
+            }
+        }
+    }
+}
+
+// camera wedge for the FOV test: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W
+__device__ __noinline__ void prepare_wedge(const FusedArgs& A, const double* __restrict__ lcal, const double* __restrict__ ccal,
+                                           const double* __restrict__ K, float* __restrict__ wq) {
+    double Rl[9], Rc[9];
+    quat_to_rot(lcal + 3, Rl);
+    quat_to_rot(ccal + 3, Rc);
+    const double d0 = ccal[0] - lcal[0], d1 = ccal[1] - lcal[1], d2 = ccal[2] - lcal[2];
+    const double ox = (Rl[0] * d0 + Rl[3] * d1) + Rl[6] * d2;
+    const double oy = (Rl[1] * d0 + Rl[4] * d1) + Rl[7] * d2;
+    const double fx = K[0], cxp = K[2];
+    const double dl[3] = {(0.0 - cxp) / fx, 0.0, 1.0};
+    const double dr[3] = {((double)A.P.image_w - cxp) / fx, 0.0, 1.0};
+    double le[3], re[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        le[r] = (Rc[r * 3 + 0] * dl[0] + Rc[r * 3 + 1] * dl[1]) + Rc[r * 3 + 2] * dl[2];
+        re[r] = (Rc[r * 3 + 0] * dr[0] + Rc[r * 3 + 1] * dr[1]) + Rc[r * 3 + 2] * dr[2];
+    }
+    wq[0] = (float)ox; wq[1] = (float)oy;
+    wq[2] = (float)((Rl[0] * le[0] + Rl[3] * le[1]) + Rl[6] * le[2]);
+    wq[3] = (float)((Rl[1] * le[0] + Rl[4] * le[1]) + Rl[7] * le[2]);
+    wq[4] = (float)((Rl[0] * re[0] + Rl[3] * re[1]) + Rl[6] * re[2]);
+    wq[5] = (float)((Rl[1] * re[0] + Rl[4] * re[1]) + Rl[7] * re[2]);
+}
+
+// exact wedge test (the definition): q = p - apex, cross(e_right, q) >= 0 and cross(q, e_left) >= 0
+__device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
+    const float qx = __fsub_rn(x, wq[0]), qy = __fsub_rn(y, wq[1]);
+    const float cr = __fmaf_rn(wq[4], qy, -__fmul_rn(wq[5], qx));
+    const float cl = __fmaf_rn(qx, wq[3], -__fmul_rn(qy, wq[2]));
+    return (cr >= 0.0f) && (cl >= 0.0f);
+}
+
+// classify one cull cell against one wedge: bit0 = every point of the cell is inside, bit1 = undecided
+__device__ __forceinline__ uint32_t classify_cell(const float* __restrict__ wq, float x0, float x1, float y0, float y1) {
+    // both cross products are affine in (x, y): extremes over the rectangle are at its corners.  The float
+    // evaluation error of the exact test is < 1e-4 for |p| < 128 m, far inside the 2e-3 guard band.
+    const float guard = 2e-3f;
+    float cr_min = INFINITY, cr_max = -INFINITY, cl_min = INFINITY, cl_max = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float qx = ((k & 1) ? x1 : x0) - wq[0], qy = ((k & 2) ? y1 : y0) - wq[1];
+        const float cr = wq[4] * qy - wq[5] * qx, cl = qx * wq[3] - qy * wq[2];
+        cr_min = fminf(cr_min, cr); cr_max = fmaxf(cr_max, cr);
+        cl_min = fminf(cl_min, cl); cl_max = fmaxf(cl_max, cl);
+    }
+    if (cr_min > guard && cl_min > guard) return 1u;    // inside
+    if (cr_max < -guard || cl_max < -guard) return 0u;  // outside
+    return 2u;                                          // straddling: run the exact test per point
+}
+
+template <class C, bool FOV, bool FASTDIV>
+__global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __grid_constant__ FusedArgs A) {
+    constexpr int NT = C::kThreads, S = C::kStages, TP = C::kTilePts, PPT = C::kPtsPerThread;
     extern __shared__ __align__(128) unsigned char smem[];
     const msc_params& P = A.P;
     const FusedLayout& L = A.L;
     float* const tiles = reinterpret_cast<float*>(smem + L.tiles_off);
     uint2* const window = reinterpret_cast<uint2*>(smem + L.window_off);
-    uint32_t* const cull = reinterpret_cast<uint32_t*>(smem + L.cull_off);
-    float* const boxp = reinterpret_cast<float*>(smem + L.boxp_off);         // [max_boxes][16]
-    uint32_t* const boxacc = reinterpret_cast<uint32_t*>(smem + L.boxacc_off); // [max_boxes][8]
+    uint2* const cull = reinterpret_cast<uint2*>(smem + L.cull_off);            // .x box ids, .y wedge classes
+    float* const boxp = reinterpret_cast<float*>(smem + L.boxp_off);            // [max_boxes][kBoxStride]
+    uint32_t* const boxacc = reinterpret_cast<uint32_t*>(smem + L.boxacc_off);  // [max_boxes][kAccWords]
     Misc* const misc = reinterpret_cast<Misc*>(smem + L.misc_off);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    const bool is_producer = tid >= NT;  // the last warpgroup only feeds the TMA ring (its first warp)
     const int res = P.bev_res, res_m1 = P.bev_res - 1;
-    const float bev_r = P.bev_range, two_r = __fmul_rn(2.0f, P.bev_range), resf = (float)P.bev_res;
     const size_t ncell = (size_t)res * (size_t)res;
-    const float cscale = (float)(1 << P.centroid_shift);
-    const float iscale = (float)(1 << P.intensity_shift);
     const int n_cams = P.n_cams;
-    const uint64_t policy = l2_policy_evict_first();
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&misc->full_bar[s], 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&misc->full_bar[s], 1); mbar_init(&misc->empty_bar[s], C::kWarps); }
         mbar_fence_init();
     }
-    uint32_t gk = 0;  // tiles consumed by this CTA since launch (ring position and mbarrier parity)
     __syncthreads();
+    constexpr int kBlock = C::kBlock;
+    auto block_sync = [] { asm volatile("bar.sync 0, %0;" ::"n"(kBlock) : "memory"); };  // all roles, from either code path
 
+    if (is_producer) {
+        // ============================================================== TMA producer warpgroup
+        reg_dealloc<C::kRegsProducer>();
+        const uint64_t policy = l2_policy_evict_first();
+        uint32_t g = 0;  // tiles requested since launch (ring position and mbarrier parity)
+        for (;;) {
+            if (tid == NT) misc->sample = (int32_t)atomicAdd(A.work_counter, 1u);
+            block_sync();  // (1) sample id published
+            const int sample = misc->sample;
+            block_sync();  // (2) everyone has read it
+            if (sample >= A.in.n_samples) break;
+            if (tid >= NT + 32) continue;  // idle warps of the producer warpgroup
+            const int sw0 = A.in.sample_sweep_off[sample], sw1 = A.in.sample_sweep_off[sample + 1];
+            for (int s = sw0; s < sw1; ++s) {
+                const uint32_t cnt = A.in.sweep_count[s];
+                const float* base = A.in.points + (size_t)A.in.sweep_start[s] * 5;
+                for (uint32_t first = 0; first < cnt; first += TP, ++g) {
+                    if (lane == 0) {
+                        const int stage = (int)(g % S);
+                        const uint32_t use = g / S;
+                        if (use >= 1) mbar_wait_parity(&misc->empty_bar[stage], (use - 1) & 1u);  // consumers released the slot
+                        const uint32_t npts = min((uint32_t)TP, cnt - first);
+                        const uint32_t bytes = (npts * 20u + 15u) & ~15u;
+                        mbar_arrive_expect_tx(&misc->full_bar[stage], bytes);
+                        bulk_load(tiles + (size_t)stage * (C::kTileBytes / 4), base + (size_t)first * 5, bytes, &misc->full_bar[stage], policy);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================================================== consumer warpgroups
+    reg_alloc<C::kRegsConsumer>();
+    uint32_t gk = 0;  // tiles consumed since launch (ring position and mbarrier parity)
     for (;;) {
-        // ------------------------------------------------------------ fetch a sample
-        if (tid == 0) misc->sample = (int32_t)atomicAdd(A.work_counter, 1u);
-        __syncthreads();
+        block_sync();  // (1)
         const int sample = misc->sample;
+        block_sync();  // (2)
         if (sample >= A.in.n_samples) break;
-
         const int sw0 = A.in.sample_sweep_off[sample], sw1 = A.in.sample_sweep_off[sample + 1];
+        uint32_t total_tiles = 0, n_in = 0;
+        for (int s = sw0; s < sw1; ++s) {
+            const uint32_t c = A.in.sweep_count[s];
+            total_tiles += (c + TP - 1) / TP;
+            n_in += c;
+        }
+
+        // -------------------------------------------------------------- consumers
         const int bx0 = A.in.sample_box_off[sample];
         int n_boxes = A.in.sample_box_off[sample + 1] - bx0;
         const bool box_overflow = n_boxes > L.max_boxes;  // caller under-declared max_boxes_per_sample
         if (box_overflow) n_boxes = L.max_boxes;
-        uint32_t total_tiles = 0, n_in = 0;
-        for (int s = sw0; s < sw1; ++s) {
-            uint32_t c = A.in.sweep_count[s];
-            total_tiles += (c + kTilePts - 1) / kTilePts;
-            n_in += c;
-        }
-
-        // producer cursor (thread 0 only): next tile to request
-        const uint32_t g_base = gk;  // ring position of this sample's tile 0
-        int p_sweep = sw0;
-        uint32_t p_tile = 0, p_issued = 0;
-        auto issue_next = [&]() {
-            // skip exhausted (or empty) sweeps
-            while (p_sweep < sw1 && p_tile * kTilePts >= A.in.sweep_count[p_sweep]) { ++p_sweep; p_tile = 0; }
-            if (p_sweep >= sw1) return;
-            const uint32_t cnt = A.in.sweep_count[p_sweep];
-            const uint32_t first = p_tile * kTilePts;
-            const uint32_t npts = min((uint32_t)kTilePts, cnt - first);
-            const uint32_t bytes = (npts * 20u + 15u) & ~15u;
-            const int stage = (int)((g_base + p_issued) % kStages);
-            const float* src = A.in.points + ((size_t)A.in.sweep_start[p_sweep] + first) * 5;
-            mbar_arrive_expect_tx(&misc->full_bar[stage], bytes);
-            bulk_load(tiles + (size_t)stage * (kTileBytes / 4), src, bytes, &misc->full_bar[stage], policy);
-            ++p_tile;
-            ++p_issued;
-        };
-        if (tid == 0) {
-            for (int s = 0; s < kStages - 1; ++s) issue_next();  // overlaps the prologue below
-        }
-
-        // ------------------------------------------------------------ prologue
         uint32_t* const g_ci = A.out.bev_ci + (size_t)sample * ncell * 2;
         float* const g_h = A.out.bev_height + (size_t)sample * ncell;
+        const double* const ego = A.in.ego_pose + (size_t)sample * 7;
+        const double* const lcal = A.in.lidar_calib + (size_t)sample * 7;
         {
-            // zero the smem accumulators
             uint4* w4 = reinterpret_cast<uint4*>(window);
             const int n_w4 = (L.win_w * L.win_w * 8) / 16;
-            for (int i = tid; i < n_w4; i += kThreads) w4[i] = make_uint4(0, 0, 0, 0);
-            const int n_cull = L.cull_dim * L.cull_dim * MASK_WORDS;
-            for (int i = tid; i < n_cull; i += kThreads) cull[i] = 0u;
-            for (int i = tid; i < n_boxes * 8; i += kThreads) boxacc[i] = ((i & 7) == 1) ? 0x7f800000u : 0u;
+            for (int i = tid; i < n_w4; i += NT) w4[i] = make_uint4(0, 0, 0, 0);
+            const int n_cull = L.cull_dim * L.cull_dim;
+            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(kCullEmpty, 0u);
+            for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
             if (tid < MSC_STATS_STRIDE) misc->stats[tid] = 0u;
-            // zero-fill this sample's global layers (cells inside the window are overwritten by the flush;
-            // zero-filling them too keeps the stores fully coalesced)
-            uint4* c4 = reinterpret_cast<uint4*>(g_ci);
-            for (size_t i = tid; i < ncell / 2; i += kThreads) c4[i] = make_uint4(0, 0, 0, 0);
-            uint4* h4 = reinterpret_cast<uint4*>(g_h);
-            for (size_t i = tid; i < ncell / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
-            if ((ncell & 3) != 0 && tid == 0) {
-                for (size_t i = (ncell / 2) * 4; i < ncell * 2; ++i) g_ci[i] = 0u;
-                for (size_t i = (ncell / 4) * 4; i < ncell; ++i) g_h[i] = 0.0f;
+            if (tid < kMaxSweepsSmem && sw0 + tid < sw1) {
+                misc->sweep_start[tid] = A.in.sweep_start[sw0 + tid];
+                misc->sweep_count[tid] = A.in.sweep_count[sw0 + tid];
             }
+            // zero-fill this sample's global layers (window cells are overwritten by the flush; filling them too
+            // keeps the stores fully coalesced)
+            uint4* c4 = reinterpret_cast<uint4*>(g_ci);
+            for (size_t i = tid; i < ncell / 2; i += NT) c4[i] = make_uint4(0, 0, 0, 0);
+            uint4* h4 = reinterpret_cast<uint4*>(g_h);
+            for (size_t i = tid; i < ncell / 4; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
+            if (FOV && tid < n_cams)
+                prepare_wedge(A, lcal, A.in.cam_calib + ((size_t)sample * n_cams + tid) * 7, A.in.cam_K + ((size_t)sample * n_cams + tid) * 9,
+                              misc->wedge[tid]);
         }
         __threadfence();
-        __syncthreads();
+        consumer_sync<NT>();
         {
-            const double* ego = A.in.ego_pose + (size_t)sample * 7;
-            const double* lcal = A.in.lidar_calib + (size_t)sample * 7;
-            // box preparation: global -> ego -> sensor, devkit points_in_box vectors (App. A.2)
-            for (int b = tid; b < n_boxes; b += kThreads) {
-                const double* box = A.in.boxes + (size_t)(bx0 + b) * 10;
-                double c[3] = {box[0], box[1], box[2]};
-                double R[9];
-                quat_to_rot(box + 6, R);
-                frame_change(ego, c, R);
-                frame_change(lcal, c, R);
-                const double w = box[3], l = box[4], h = box[5];
-                const double hl = l / 2.0, hw = w / 2.0, hh = h / 2.0;
-                float* o = boxp + b * 16;
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    o[r] = (float)(((R[r * 3 + 0] * hl + R[r * 3 + 1] * hw) + R[r * 3 + 2] * hh) + c[r]);
-                    o[3 + r] = (float)(-(l * R[r * 3 + 0]));
-                    o[6 + r] = (float)(-(w * R[r * 3 + 1]));
-                    o[9 + r] = (float)(-(h * R[r * 3 + 2]));
+            for (int b = tid; b < n_boxes; b += NT) prepare_box(A, A.in.boxes + (size_t)(bx0 + b) * 10, ego, lcal, b, boxp, cull);
+            if (FOV) {
+                // per cull cell: which cameras contain the whole cell (bits 0-7) and which need the exact test (8-15)
+                const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
+                const int last = L.cull_dim - 1;
+                const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
+                for (int i = tid; i < L.cull_dim * L.cull_dim; i += NT) {
+                    const int gy = i / L.cull_dim, gx = i - gy * L.cull_dim;
+                    // edge cells absorb everything clipped into them
+                    const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
+                    const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
+                    const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
+                    const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
+                    uint32_t bits = 0;
+                    for (int c = 0; c < n_cams; ++c) {
+                        const uint32_t k = classify_cell(misc->wedge[c], x0, x1, y0, y1);
+                        bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
+                    }
+                    cull[i].y = bits;
                 }
-                o[12] = __fmaf_rn(o[5], o[5], __fmaf_rn(o[4], o[4], __fmul_rn(o[3], o[3])));
-                o[13] = __fmaf_rn(o[8], o[8], __fmaf_rn(o[7], o[7], __fmul_rn(o[6], o[6])));
-                o[14] = __fmaf_rn(o[11], o[11], __fmaf_rn(o[10], o[10], __fmul_rn(o[9], o[9])));
-                o[15] = 0.0f;
-                // conservative cull-grid rasterisation: xy bounding box of the 8 corners, 1 mm margin.
-                // Every member point lies in the corner hull up to float rounding (<< 1 mm), and
-                // bev_index() is monotonic, so no member can fall outside the marked cells.
-                float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const double lx = (k < 4) ? hl : -hl;
-                    const double ly = (k == 0 || k == 3 || k == 4 || k == 7) ? hw : -hw;
-                    const double lz = (k == 0 || k == 1 || k == 4 || k == 5) ? hh : -hh;
-                    float cx = (float)(((R[0] * lx + R[1] * ly) + R[2] * lz) + c[0]);
-                    float cy = (float)(((R[3] * lx + R[4] * ly) + R[5] * lz) + c[1]);
-                    xmin = fminf(xmin, cx); xmax = fmaxf(xmax, cx);
-                    ymin = fminf(ymin, cy); ymax = fmaxf(ymax, cy);
-                }
-                const int cx0 = bev_index(xmin - 1e-3f, bev_r, two_r, resf, res_m1) >> L.cull_shift;
-                const int cx1 = bev_index(xmax + 1e-3f, bev_r, two_r, resf, res_m1) >> L.cull_shift;
-                const int cy0 = bev_index(ymin - 1e-3f, bev_r, two_r, resf, res_m1) >> L.cull_shift;
-                const int cy1 = bev_index(ymax + 1e-3f, bev_r, two_r, resf, res_m1) >> L.cull_shift;
-                const uint32_t bit = 1u << (b & 31);
-                for (int cy = cy0; cy <= cy1; ++cy)
-                    for (int cx = cx0; cx <= cx1; ++cx) atomicOr(&cull[(cy * L.cull_dim + cx) * MASK_WORDS + (b >> 5)], bit);
-            }
-            // camera wedges for the FOV test (apex = camera centre, edges = image columns 0 and W)
-            if (FOV && tid < n_cams) {
-                const double* ccal = A.in.cam_calib + ((size_t)sample * n_cams + tid) * 7;
-                const double* K = A.in.cam_K + ((size_t)sample * n_cams + tid) * 9;
-                double Rl[9], Rc[9];
-                quat_to_rot(lcal + 3, Rl);
-                quat_to_rot(ccal + 3, Rc);
-                const double d0 = ccal[0] - lcal[0], d1 = ccal[1] - lcal[1], d2 = ccal[2] - lcal[2];
-                const double ox = (Rl[0] * d0 + Rl[3] * d1) + Rl[6] * d2;
-                const double oy = (Rl[1] * d0 + Rl[4] * d1) + Rl[7] * d2;
-                const double fx = K[0], cxp = K[2];
-                const double dl[3] = {(0.0 - cxp) / fx, 0.0, 1.0};
-                const double dr[3] = {((double)P.image_w - cxp) / fx, 0.0, 1.0};
-                double le[3], re[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    le[r] = (Rc[r * 3 + 0] * dl[0] + Rc[r * 3 + 1] * dl[1]) + Rc[r * 3 + 2] * dl[2];
-                    re[r] = (Rc[r * 3 + 0] * dr[0] + Rc[r * 3 + 1] * dr[1]) + Rc[r * 3 + 2] * dr[2];
-                }
-                float* wq = misc->wedge[tid];
-                wq[0] = (float)ox; wq[1] = (float)oy;
-                wq[2] = (float)((Rl[0] * le[0] + Rl[3] * le[1]) + Rl[6] * le[2]);
-                wq[3] = (float)((Rl[1] * le[0] + Rl[4] * le[1]) + Rl[7] * le[2]);
-                wq[4] = (float)((Rl[0] * re[0] + Rl[3] * re[1]) + Rl[6] * re[2]);
-                wq[5] = (float)((Rl[1] * re[0] + Rl[4] * re[1]) + Rl[7] * re[2]);
             }
             // box -> camera projection (App. A.3), one (box, camera) pair per thread
             const double Wd = (double)P.image_w, Hd = (double)P.image_h;
-            for (int t = tid; t < n_boxes * n_cams; t += kThreads) {
+            for (int t = tid; t < n_boxes * n_cams; t += NT) {
                 const int b = t / n_cams, c = t - b * n_cams;
                 const size_t o = (size_t)(bx0 + b) * n_cams + c;
                 project_box(A.in.boxes + (size_t)(bx0 + b) * 10, A.in.cam_ego_pose + ((size_t)sample * n_cams + c) * 7,
@@ -247,141 +386,161 @@ __global__ void __launch_bounds__(kThreads, 1) fused_evidence_kernel(const __gri
                             Hd, A.out.proj_visible + o, A.out.proj_extent + o * 4);
             }
         }
-        __syncthreads();
+        consumer_sync<NT>();
 
-        // ------------------------------------------------------------ main loop over tiles
-        uint32_t c_close = 0, c_kept = 0, c_ground = 0;  // per-thread counters
-        uint32_t c_cam[FOV ? MSC_MAX_CAMS : 1];
-#pragma unroll
-        for (int c = 0; c < (FOV ? MSC_MAX_CAMS : 1); ++c) c_cam[c] = 0;
+        // ------------------------------------------------------------ main loop over tiles (no CTA-wide barrier)
+        uint32_t c_close = 0, c_kept = 0, c_ground = 0;  // per-thread counters (flushed once per sample)
+        uint32_t cam_lo = 0, cam_hi = 0;                 // eight 8-bit per-camera counters, spilled every <= 255 points
+        uint32_t cam_pts = 0;
 
-        int c_sweep = sw0;
-        uint32_t c_tile = 0;
+        int c_sweep = 0;  // index into this sample's sweeps
+        uint32_t c_first = 0;
+        uint32_t cur_cnt = 0;
         double M[12];
         bool have_pose = false;
+        auto sweep_cnt = [&](int si) -> uint32_t { return si < kMaxSweepsSmem ? misc->sweep_count[si] : A.in.sweep_count[sw0 + si]; };
+        cur_cnt = (sw1 > sw0) ? sweep_cnt(0) : 0u;
         for (uint32_t k = 0; k < total_tiles; ++k) {
-            if (tid == 0) issue_next();
-            while (c_tile * kTilePts >= A.in.sweep_count[c_sweep]) { ++c_sweep; c_tile = 0; have_pose = false; }
+            while (c_first >= cur_cnt) { ++c_sweep; c_first = 0; cur_cnt = sweep_cnt(c_sweep); have_pose = false; }
             if (!have_pose) {
-                const double* Mp = A.in.sweep_pose + (size_t)c_sweep * 12;
-#pragma unroll
-                for (int i = 0; i < 12; ++i) M[i] = __ldg(Mp + i);
+                ld_pose(A.in.sweep_pose + (size_t)(sw0 + c_sweep) * 12, M);
                 have_pose = true;
             }
-            const uint32_t first = c_tile * kTilePts;
-            const uint32_t npts = min((uint32_t)kTilePts, A.in.sweep_count[c_sweep] - first);
-            const int stage = (int)(gk % kStages);
-            mbar_wait_parity(&misc->full_bar[stage], (gk / kStages) & 1u);
-            const float* tp = tiles + (size_t)stage * (kTileBytes / 4);
+            const uint32_t npts = min((uint32_t)TP, cur_cnt - c_first);
+            const int stage = (int)(gk % S);
+            mbar_wait_parity(&misc->full_bar[stage], (gk / S) & 1u);
+            const float* tp = tiles + (size_t)stage * (C::kTileBytes / 4) + tid * 5;
 
+            // ---- phase A: branch-free over the thread's PPT points so their dependency chains interleave
+            float xr[PPT], yr[PPT], zr[PPT], s2[PPT], inten[PPT];
+            int ix[PPT], iy[PPT];
+            uint2 ce[PPT];
+            bool alive[PPT], keep[PPT];
 #pragma unroll
-            for (int u = 0; u < kPtsPerThread; ++u) {
-                const uint32_t p = (uint32_t)tid + (uint32_t)u * kThreads;
-                if (p < npts) {
-                    const float x = tp[p * 5 + 0], y = tp[p * 5 + 1], z = tp[p * 5 + 2], inten = tp[p * 5 + 3];
-                    // A.1 remove_close (square, sweep's own sensor frame)
-                    if (!(fabsf(x) < P.remove_close_radius && fabsf(y) < P.remove_close_radius)) {
-                        ++c_close;
-                        // A.1 f64 matrix x f32 point -> f32
-                        const double xd = (double)x, yd = (double)y, zd = (double)z;
-                        const float xr = (float)__fma_rn(M[0], xd, __fma_rn(M[1], yd, __fma_rn(M[2], zd, M[3])));
-                        const float yr = (float)__fma_rn(M[4], xd, __fma_rn(M[5], yd, __fma_rn(M[6], zd, M[7])));
-                        const float zr = (float)__fma_rn(M[8], xd, __fma_rn(M[9], yd, __fma_rn(M[10], zd, M[11])));
-                        // lidar_agent.py:106-110, sqrt-free (thresholds on s are exact, geometry.sqrt_thresholds)
-                        const float s2 = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr));
-                        bool keep = (s2 >= P.s_lo) && (s2 <= P.s_hi) && (zr < P.z_max) && (zr > P.z_min);
-                        if (FOV && keep) {
-                            uint32_t cam_bits = 0;
+            for (int u = 0; u < PPT; ++u) {
+                const bool valid = (uint32_t)tid + (uint32_t)u * NT < npts;
+                const float x = tp[u * NT * 5 + 0], y = tp[u * NT * 5 + 1], z = tp[u * NT * 5 + 2];
+                inten[u] = tp[u * NT * 5 + 3];
+                // A.1 remove_close (square, sweep's own sensor frame)
+                alive[u] = valid && !(fabsf(x) < P.remove_close_radius && fabsf(y) < P.remove_close_radius);
+                // A.1 f64 matrix x f32 point -> f32
+                const double xd = (double)x, yd = (double)y, zd = (double)z;
+                xr[u] = (float)__fma_rn(M[0], xd, __fma_rn(M[1], yd, __fma_rn(M[2], zd, M[3])));
+                yr[u] = (float)__fma_rn(M[4], xd, __fma_rn(M[5], yd, __fma_rn(M[6], zd, M[7])));
+                zr[u] = (float)__fma_rn(M[8], xd, __fma_rn(M[9], yd, __fma_rn(M[10], zd, M[11])));
+                // lidar_agent.py:106-110, sqrt-free (thresholds on s are exact, geometry.sqrt_thresholds)
+                s2[u] = __fadd_rn(__fmul_rn(xr[u], xr[u]), __fmul_rn(yr[u], yr[u]));
+                keep[u] = alive[u] && (s2[u] >= P.s_lo) && (s2[u] <= P.s_hi) && (zr[u] < P.z_max) && (zr[u] > P.z_min);
+                // BEV cell, lidar_agent.py:547-552 (garbage for dropped points is clamped and never used)
+                ix[u] = bev_cell<FASTDIV>(xr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
+                iy[u] = bev_cell<FASTDIV>(yr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
+                ce[u] = cull[(iy[u] >> L.cull_shift) * L.cull_dim + (ix[u] >> L.cull_shift)];
+                c_close += alive[u] ? 1u : 0u;
+            }
+            // ---- phase B: data-dependent work per kept point
 #pragma unroll
-                            for (int c = 0; c < MSC_MAX_CAMS; ++c) {
-                                if (c < n_cams) {
-                                    const float* wq = misc->wedge[c];
-                                    const float qx = __fsub_rn(xr, wq[0]), qy = __fsub_rn(yr, wq[1]);
-                                    const float cr = __fmaf_rn(wq[4], qy, -__fmul_rn(wq[5], qx));
-                                    const float cl = __fmaf_rn(qx, wq[3], -__fmul_rn(qy, wq[2]));
-                                    const bool in = (cr >= 0.0f) && (cl >= 0.0f);
-                                    c_cam[c] += in ? 1u : 0u;
-                                    cam_bits |= in ? (1u << c) : 0u;
-                                }
-                            }
-                            if (P.fov_keep_mask != 0u && (cam_bits & P.fov_keep_mask) == 0u) keep = false;
-                        }
-                        if (keep) {
-                            ++c_kept;
-                            c_ground += (zr < P.ground_z) ? 1u : 0u;  // lidar_agent.py:128
-                            // BEV cell, lidar_agent.py:547-552
-                            const int ix = bev_index(xr, bev_r, two_r, resf, res_m1);
-                            const int iy = bev_index(yr, bev_r, two_r, resf, res_m1);
-                            // Q8 intensity, clamp [0, 65535]; NaN -> 0
-                            float qf = __fmul_rn(inten, iscale);
-                            qf = fminf(fmaxf(qf, 0.0f), 65535.0f);
-                            const uint32_t q = (uint32_t)__float2int_rn(qf);
-                            const uint32_t wx = (uint32_t)(ix - L.win_lo), wy = (uint32_t)(iy - L.win_lo);
-                            const size_t cell = (size_t)iy * (size_t)res + (size_t)ix;
-                            if (wx < (uint32_t)L.win_w && wy < (uint32_t)L.win_w) {
-                                uint2* wc = window + wy * (uint32_t)L.win_w + wx;
-                                atomicAdd(&wc->x, 1u);
-                                atomicAdd(&wc->y, q);
-                            } else {
-                                atomicAdd(reinterpret_cast<unsigned long long*>(g_ci) + cell, 1ull | ((unsigned long long)q << 32));
-                            }
-                            if (zr > 0.0f) atomicMax(reinterpret_cast<int*>(g_h) + cell, __float_as_int(zr));  // :560, 0-initialised max
-                            // A.2 oriented-box membership through the cull grid
-                            const uint32_t* cm = cull + ((iy >> L.cull_shift) * L.cull_dim + (ix >> L.cull_shift)) * MASK_WORDS;
-#pragma unroll
-                            for (int w = 0; w < MASK_WORDS; ++w) {
-                                uint32_t m = cm[w];
-                                while (m) {
-                                    const int b = w * 32 + (__ffs((int)m) - 1);
-                                    m &= m - 1;
-                                    const float4 b0 = reinterpret_cast<const float4*>(boxp + b * 16)[0];
-                                    const float4 b1 = reinterpret_cast<const float4*>(boxp + b * 16)[1];
-                                    const float4 b2 = reinterpret_cast<const float4*>(boxp + b * 16)[2];
-                                    const float4 b3 = reinterpret_cast<const float4*>(boxp + b * 16)[3];
-                                    const float v0 = __fsub_rn(xr, b0.x), v1 = __fsub_rn(yr, b0.y), v2 = __fsub_rn(zr, b0.z);
-                                    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
-                                    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
-                                    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
-                                    if (iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z) {
-                                        uint32_t* acc = boxacc + b * 8;
-                                        atomicAdd(acc + 0, 1u);
-                                        atomicMin(acc + 1, __float_as_uint(s2));
-                                        smem_add_s64(acc + 2, __float2int_rn(__fmul_rn(xr, cscale)));
-                                        smem_add_s64(acc + 4, __float2int_rn(__fmul_rn(yr, cscale)));
-                                        smem_add_s64(acc + 6, __float2int_rn(__fmul_rn(zr, cscale)));
-                                    }
-                                }
-                            }
-                        }
+            for (int u = 0; u < PPT; ++u) {
+                if (!keep[u]) continue;
+                if (FOV) {
+                    uint32_t in_bits = ce[u].y & 0xffu;
+                    uint32_t st = ce[u].y >> 8;
+                    while (st) {  // exact wedge test only where the cell straddles a wedge edge
+                        const int c = __ffs((int)st) - 1;
+                        st &= st - 1;
+                        in_bits |= in_wedge(misc->wedge[c], xr[u], yr[u]) ? (1u << c) : 0u;
+                    }
+                    // spread 8 bits into 8 byte counters (no carries: the multiplier's partial products do not overlap)
+                    cam_lo += ((in_bits & 0xfu) * 0x00204081u) & 0x01010101u;
+                    cam_hi += ((in_bits >> 4) * 0x00204081u) & 0x01010101u;
+                    if (P.fov_keep_mask != 0u && (in_bits & P.fov_keep_mask) == 0u) continue;
+                }
+                ++c_kept;
+                c_ground += (zr[u] < P.ground_z) ? 1u : 0u;  // lidar_agent.py:128
+                // Q8 intensity, clamp [0, 65535]; NaN -> 0
+                const float qf = fminf(fmaxf(__fmul_rn(inten[u], A.iscale), 0.0f), 65535.0f);
+                const uint32_t q = (uint32_t)__float2int_rn(qf);
+                const uint32_t wx = (uint32_t)(ix[u] - L.win_lo), wy = (uint32_t)(iy[u] - L.win_lo);
+                const uint32_t cell = (uint32_t)iy[u] * (uint32_t)res + (uint32_t)ix[u];
+                if (wx < (uint32_t)L.win_w && wy < (uint32_t)L.win_w) {
+                    uint2* wc = window + wy * (uint32_t)L.win_w + wx;
+                    if (!(A.debug_skip & 4u)) {
+                        atomicAdd(&wc->x, 1u);
+                        atomicAdd(&wc->y, q);
+                    }
+                } else if (!(A.debug_skip & 1u)) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(g_ci) + cell, 1ull | ((unsigned long long)q << 32));
+                }
+                if (zr[u] > 0.0f && !(A.debug_skip & 1u)) atomicMax(reinterpret_cast<int*>(g_h) + cell, __float_as_int(zr[u]));  // :560, 0-initialised max
+                // A.2 oriented-box membership for the candidate boxes of this cull cell
+                uint32_t ids = ce[u].x;
+                if (ids == kCullEmpty || (A.debug_skip & 2u)) continue;
+                int b_all = (ids == kCullAll) ? 0 : -1;  // >= 0: crowded cell, test every box
+                for (;;) {
+                    int b;
+                    if (b_all >= 0) {
+                        if (b_all >= n_boxes) break;
+                        b = b_all++;
+                    } else {
+                        b = (int)(ids & 0xffu);
+                        if (b == 0xff) break;
+                        ids = (ids >> 8) | 0xff000000u;
+                    }
+                    const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
+                    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+                    const float v0 = __fsub_rn(xr[u], b0.x), v1 = __fsub_rn(yr[u], b0.y), v2 = __fsub_rn(zr[u], b0.z);
+                    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
+                    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
+                    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
+                    if (iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z && !(A.debug_skip & 8u)) {
+                        uint32_t* acc = boxacc + b * kAccWords;
+                        atomicAdd(acc + 0, 1u);
+                        atomicMin(acc + 1, __float_as_uint(s2[u]));
+                        // fixed-point centroid sums: non-negative biased value split into three 9-bit limbs
+                        const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr[u], A.cscale)) + A.centroid_bias);
+                        const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr[u], A.cscale)) + A.centroid_bias);
+                        const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr[u], A.cscale)) + A.centroid_bias);
+                        atomicAdd(acc + 2, qx & 511u); atomicAdd(acc + 3, (qx >> 9) & 511u); atomicAdd(acc + 4, qx >> 18);
+                        atomicAdd(acc + 5, qy & 511u); atomicAdd(acc + 6, (qy >> 9) & 511u); atomicAdd(acc + 7, qy >> 18);
+                        atomicAdd(acc + 8, qz & 511u); atomicAdd(acc + 9, (qz >> 9) & 511u); atomicAdd(acc + 10, qz >> 18);
                     }
                 }
             }
+            // release the stage to the producer: one arrival per consumer warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&misc->empty_bar[stage]);
             ++gk;
-            ++c_tile;
-            __syncthreads();  // every thread is done with this stage -> thread 0 may refill it next iteration
+            c_first += TP;
+            if (FOV) {
+                cam_pts += PPT;
+                if (cam_pts > 255u - PPT) {  // spill the byte counters before any of them can wrap
+#pragma unroll
+                    for (int c = 0; c < MSC_MAX_CAMS; ++c) {
+                        const uint32_t v = ((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu;
+                        if (v) atomicAdd(&misc->stats[5 + c], v);
+                    }
+                    cam_lo = cam_hi = cam_pts = 0;
+                }
+            }
         }
 
         // ------------------------------------------------------------ epilogue
         {
-            // per-thread counters -> warp reduce -> smem
-            uint32_t v[3 + (FOV ? MSC_MAX_CAMS : 0)];
+            uint32_t v[3 + MSC_MAX_CAMS];
             v[0] = c_close; v[1] = c_kept; v[2] = c_ground;
-            if (FOV) {
 #pragma unroll
-                for (int c = 0; c < MSC_MAX_CAMS; ++c) v[3 + c] = c_cam[c];
-            }
+            for (int c = 0; c < MSC_MAX_CAMS; ++c) v[3 + c] = FOV ? (((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu) : 0u;
 #pragma unroll
             for (int i = 0; i < 3 + (FOV ? MSC_MAX_CAMS : 0); ++i) {
-                uint32_t r = __reduce_add_sync(0xffffffffu, v[i]);
-                if ((tid & 31) == 0 && r) atomicAdd(&misc->stats[i < 3 ? 1 + i : 2 + i], r);
+                const uint32_t r = __reduce_add_sync(0xffffffffu, v[i]);
+                if (lane == 0 && r) atomicAdd(&misc->stats[i < 3 ? 1 + i : 2 + i], r);
             }
         }
-        __syncthreads();
+        consumer_sync<NT>();  // every tile of the sample is accumulated
         {
             // window flush: coalesced 16-byte stores of (count, isum) pairs, two cells per store
-            const int half_w = L.win_w >> 1;  // win_w is even and win_lo is even -> 16-byte aligned rows
+            const int half_w = L.win_w >> 1;  // win_w and win_lo are even -> 16-byte aligned rows
             uint32_t flags = 0;
-            for (int i = tid; i < L.win_w * half_w; i += kThreads) {
+            for (int i = tid; i < L.win_w * half_w; i += NT) {
                 const int wy = i / half_w, wx2 = i - wy * half_w;
                 const uint4 v = reinterpret_cast<const uint4*>(window)[wy * half_w + wx2];
                 const size_t cell = (size_t)(wy + L.win_lo) * (size_t)res + (size_t)(wx2 * 2 + L.win_lo);
@@ -390,8 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_evidence_kernel(const __gri
             }
             if (flags) atomicOr(&misc->stats[13], flags);
             // per-box results
-            for (int b = tid; b < n_boxes; b += kThreads) {
-                const uint32_t* acc = boxacc + b * 8;
+            for (int b = tid; b < n_boxes; b += NT) {
+                const uint32_t* acc = boxacc + b * kAccWords;
                 const uint32_t cnt = acc[0];
                 const size_t o = (size_t)(bx0 + b);
                 A.out.box_count[o] = cnt;
@@ -400,16 +559,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_evidence_kernel(const __gri
                     A.out.box_centroid[o * 3 + 0] = 0.0f; A.out.box_centroid[o * 3 + 1] = 0.0f; A.out.box_centroid[o * 3 + 2] = 0.0f;
                 } else {
                     A.out.box_nearest[o] = __fsqrt_rn(__uint_as_float(acc[1]));
-                    const double den = (double)cnt * (double)cscale;
+                    const double den = (double)cnt * (double)A.cscale;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const long long sum = (long long)(((unsigned long long)acc[3 + 2 * k] << 32) | (unsigned long long)acc[2 + 2 * k]);
+                        const unsigned long long biased = (unsigned long long)acc[2 + 3 * k] + ((unsigned long long)acc[3 + 3 * k] << 9) +
+                                                          ((unsigned long long)acc[4 + 3 * k] << 18);
+                        const long long sum = (long long)biased - (long long)cnt * (long long)A.centroid_bias;
                         A.out.box_centroid[o * 3 + k] = (float)((double)sum / den);
                     }
                 }
             }
         }
-        __syncthreads();
+        consumer_sync<NT>();
         if (tid < MSC_STATS_STRIDE) {
             uint32_t v = misc->stats[tid];
             if (tid == 0) v = n_in;
@@ -417,27 +578,32 @@ __global__ void __launch_bounds__(kThreads, 1) fused_evidence_kernel(const __gri
             if (tid == 13 && box_overflow) v |= 0x80000000u;
             A.out.stats[(size_t)sample * MSC_STATS_STRIDE + tid] = v;
         }
-        // (the next iteration's first __syncthreads orders these reads before the smem is re-zeroed)
+        // (block_sync (1) at the top of the loop orders these reads before the next sample re-zeroes the smem)
     }
 }
-
-// out-of-window cells whose count reaches 65536 are flagged by a tiny follow-up kernel only when asked for
-// by tests; in production the window covers the dense centre and the flag above is sufficient.
 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int g_opt_fov = 1;
-static int g_opt_window = 0;  // 0 = auto (largest that fits)
+static int g_opt_window = 0;       // 0 = auto (largest that fits)
 static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
-static int g_last_window = 0, g_last_smem = 0;
+static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
+static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
+static int g_opt_debug_skip = 0;
+static int g_opt_config = 0;       // launch shape: 0 = 512 thr x 2 pts, 4 stages; 1 = 512x2, 3 stages; 2 = 384x2, 5 stages
 
-static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, FusedLayout* L, int* mask_words) {
-    int mw = (max_boxes_in_batch + 31) / 32;
-    if (mw <= 1) mw = 1; else if (mw <= 2) mw = 2; else if (mw <= 4) mw = 4; else mw = 8;
-    *mask_words = mw;
-    const int cap = mw * 32;
-    // cull cell ~ 2 m
+// divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
+static bool fastdiv_verified(float two_r) {
+    const float ok[] = {100.0f, 102.4f, 120.0f, 150.0f, 160.0f, 200.0f};
+    for (float v : ok)
+        if (two_r == v) return true;
+    int e = 0;
+    return frexpf(two_r, &e) == 0.5f;  // powers of two divide exactly either way
+}
+
+static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int stage_bytes, FusedLayout* L) {
+    const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
     const float cell_m = 2.0f * P.bev_range / (float)P.bev_res;
     int shift = 0;
     if (g_opt_cull_shift >= 0) shift = g_opt_cull_shift;
@@ -446,10 +612,11 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
     L->cull_dim = ((P.bev_res - 1) >> shift) + 1;
     L->max_boxes = cap;
     int off = 0;
-    L->tiles_off = off; off += kStages * kTileBytes;
-    L->cull_off = off; off += L->cull_dim * L->cull_dim * mw * 4; off = (off + 127) & ~127;
-    L->boxp_off = off; off += cap * 64;
-    L->boxacc_off = off; off += cap * 32;
+    L->tiles_off = off; off += stage_bytes;
+    L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
+    L->boxp_off = off; off += cap * kBoxStride * 4;
+    L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
+    L->lut_off = 0;
     L->misc_off = off; off += (int)((sizeof(Misc) + 127) & ~127);
     L->window_off = off;
     const int avail = smem_limit - off;
@@ -459,20 +626,31 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
     if (g_opt_window > 0 && g_opt_window < w) w = g_opt_window & ~1;
     if (((P.bev_res - w) / 2) & 1) w -= 2;  // keep win_lo even so flush rows stay 16-byte aligned
     if (w < 0) w = 0;
-    if (P.bev_res & 1) w = 0;               // odd resolutions: no window (all cells via global reductions)
     L->win_w = w;
     L->win_lo = (P.bev_res - w) / 2;
     L->total_bytes = off + w * w * 8;
     return 0;
 }
 
-template <int MW, bool FOV>
+template <class C, bool FOV, bool FASTDIV>
 static int launch_fused(const FusedArgs& args, int grid, cudaStream_t stream) {
-    auto kern = fused_evidence_kernel<MW, FOV>;
+    auto kern = fused_evidence_kernel<C, FOV, FASTDIV>;
     MSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, args.L.total_bytes));
-    kern<<<grid, kThreads, args.L.total_bytes, stream>>>(args);
+    kern<<<grid, C::kBlock, args.L.total_bytes, stream>>>(args);
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
+}
+template <class C>
+static int dispatch_fused(FusedArgs& args, const msc_params& P, int max_boxes, int smem_optin, int grid, bool fov, bool fast, cudaStream_t stream) {
+    if (compute_layout(P, max_boxes, smem_optin, C::kStages * C::kTileBytes, &args.L) != 0) {
+        set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
+        return MSC_ERR_UNSUPPORTED;
+    }
+    g_last_window = args.L.win_w;
+    g_last_smem = args.L.total_bytes;
+    g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
+    if (fov) return fast ? launch_fused<C, true, true>(args, grid, stream) : launch_fused<C, true, false>(args, grid, stream);
+    return fast ? launch_fused<C, false, true>(args, grid, stream) : launch_fused<C, false, false>(args, grid, stream);
 }
 
 }  // namespace msc
@@ -489,6 +667,9 @@ int msc_fused_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "fov")) { msc::g_opt_fov = value ? 1 : 0; return MSC_OK; }
     if (!strcmp(key, "window")) { msc::g_opt_window = value; return MSC_OK; }
     if (!strcmp(key, "cull_shift")) { msc::g_opt_cull_shift = value; return MSC_OK; }
+    if (!strcmp(key, "fastdiv")) { msc::g_opt_fastdiv = value ? 1 : 0; return MSC_OK; }
+    if (!strcmp(key, "config")) { msc::g_opt_config = value; return MSC_OK; }
+    if (!strcmp(key, "debug_skip")) { msc::g_opt_debug_skip = value; return MSC_OK; }
     msc::set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
 }
@@ -498,11 +679,14 @@ int msc_fused_get_option(const char* key, int32_t* value) {
     if (!strcmp(key, "fov")) { *value = msc::g_opt_fov; return MSC_OK; }
     if (!strcmp(key, "window")) { *value = msc::g_opt_window; return MSC_OK; }
     if (!strcmp(key, "cull_shift")) { *value = msc::g_opt_cull_shift; return MSC_OK; }
+    if (!strcmp(key, "fastdiv")) { *value = msc::g_opt_fastdiv; return MSC_OK; }
     if (!strcmp(key, "last_window")) { *value = msc::g_last_window; return MSC_OK; }
     if (!strcmp(key, "last_smem")) { *value = msc::g_last_smem; return MSC_OK; }
-    if (!strcmp(key, "tile_pts")) { *value = msc::kTilePts; return MSC_OK; }
-    if (!strcmp(key, "stages")) { *value = msc::kStages; return MSC_OK; }
-    if (!strcmp(key, "threads")) { *value = msc::kThreads; return MSC_OK; }
+    if (!strcmp(key, "last_fastdiv")) { *value = msc::g_last_fastdiv; return MSC_OK; }
+    if (!strcmp(key, "config")) { *value = msc::g_opt_config; return MSC_OK; }
+    if (!strcmp(key, "tile_pts")) { *value = msc::g_last_tile_pts; return MSC_OK; }
+    if (!strcmp(key, "stages")) { *value = msc::g_last_stages; return MSC_OK; }
+    if (!strcmp(key, "threads")) { *value = msc::g_last_threads; return MSC_OK; }
     msc::set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
 }
@@ -514,10 +698,11 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     MSC_REQUIRE(workspace_bytes >= 256, "workspace too small");
     MSC_REQUIRE(in->n_samples >= 0, "negative n_samples");
     MSC_REQUIRE(params->n_cams >= 0 && params->n_cams <= MSC_MAX_CAMS, "n_cams out of range");
-    MSC_REQUIRE(params->bev_res > 0 && params->bev_res <= 4096, "bev_res out of range");
-    MSC_REQUIRE(params->centroid_shift >= 0 && params->centroid_shift <= 24, "centroid_shift out of range");
+    MSC_REQUIRE(params->bev_res > 0 && params->bev_res <= 4096 && (params->bev_res & 1) == 0, "bev_res must be even and <= 4096");
+    MSC_REQUIRE(params->centroid_shift >= 0 && params->centroid_shift <= 20, "centroid_shift out of range");
     MSC_REQUIRE(params->intensity_shift >= 0 && params->intensity_shift <= 8, "intensity_shift out of range");
-    MSC_REQUIRE((params->bev_res & 1) == 0, "bev_res must be even");
+    // the biased fixed-point coordinate must fit 27 bits: |c| * 2^shift < 2^(shift + 6)  <=>  |c| < 64 m
+    MSC_REQUIRE(params->range_max < 64.0f && params->z_max < 64.0f && params->z_min > -64.0f, "range_max / z limits must be below 64 m");
     const int32_t max_boxes_per_sample = in->max_boxes_per_sample;
     MSC_REQUIRE(max_boxes_per_sample >= 0 && max_boxes_per_sample <= MSC_MAX_BOXES_FUSED, "more than %d boxes in one sample",
                 MSC_MAX_BOXES_FUSED);
@@ -533,21 +718,22 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     args.in = *in;
     args.out = *out;
     args.work_counter = reinterpret_cast<uint32_t*>(workspace);
-    int mw = 1;
-    if (compute_layout(*params, max_boxes_per_sample, smem_optin, &args.L, &mw) != 0) {
-        set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
-        return MSC_ERR_UNSUPPORTED;
-    }
-    g_last_window = args.L.win_w;
-    g_last_smem = args.L.total_bytes;
+    args.two_r = 2.0f * params->bev_range;
+    args.resf = (float)params->bev_res;
+    args.rcp_two_r = 1.0f / args.two_r;
+    args.cscale = (float)(1 << params->centroid_shift);
+    args.iscale = (float)(1 << params->intensity_shift);
+    args.centroid_bias = 1 << (params->centroid_shift + 6);
+    args.debug_skip = (uint32_t)g_opt_debug_skip;
+    const bool fov = g_opt_fov != 0 && params->n_cams > 0;
+    const bool fast = g_opt_fastdiv != 0 && fastdiv_verified(args.two_r);
+    g_last_fastdiv = fast ? 1 : 0;
     MSC_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
     const int grid = in->n_samples < sms ? in->n_samples : sms;
-    const bool fov = g_opt_fov != 0 && params->n_cams > 0;
-    switch (mw) {
-        case 1: return fov ? launch_fused<1, true>(args, grid, stream) : launch_fused<1, false>(args, grid, stream);
-        case 2: return fov ? launch_fused<2, true>(args, grid, stream) : launch_fused<2, false>(args, grid, stream);
-        case 4: return fov ? launch_fused<4, true>(args, grid, stream) : launch_fused<4, false>(args, grid, stream);
-        default: return fov ? launch_fused<8, true>(args, grid, stream) : launch_fused<8, false>(args, grid, stream);
+    switch (g_opt_config) {
+        case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
+        case 2: return dispatch_fused<Cfg<384, 2, 5>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
+        default: return dispatch_fused<Cfg<512, 2, 4>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
     }
 }
 

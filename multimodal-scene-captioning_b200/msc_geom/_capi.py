@@ -7,7 +7,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libmsc_geom.so")
 
 MSC_MAX_CAMS = 8
-MSC_MAX_BOXES_FUSED = 256
+MSC_MAX_BOXES_FUSED = 255
 MSC_STATS_STRIDE = 16
 ABI_VERSION = 1
 

@@ -103,7 +103,7 @@ class GeometryEngine:
         sm, smem, maj, mnr = (C.c_int32() for _ in range(4))
         _capi.check(self.lib.msc_device_info(C.byref(sm), C.byref(smem), C.byref(maj), C.byref(mnr)), "msc_device_info")
         self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, (maj.value, mnr.value)
-        self._workspace = torch.zeros(64, dtype=torch.int32, device=self.device)
+        self._workspaces: Dict[int, torch.Tensor] = {}  # one work counter per stream (kernels on different streams overlap)
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ transfers
@@ -138,8 +138,11 @@ class GeometryEngine:
             out = self.alloc_result(db.host, p)
         mp, bi, bo = make_params(p), db.struct(), out.struct()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), self._workspace.data_ptr(),
-                                                      self._workspace.numel() * 4, C.c_void_p(stream)), "msc_fused_evidence_batch")
+        ws = self._workspaces.get(stream)
+        if ws is None:
+            ws = self._workspaces[stream] = torch.zeros(64, dtype=torch.int32, device=self.device)
+        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel() * 4,
+                                                      C.c_void_p(stream)), "msc_fused_evidence_batch")
         self.kernel_launches += 1
         return out
 
