@@ -61,7 +61,9 @@ typedef struct {
  * points buffer must extend 16 bytes past the last sweep. */
 typedef struct {
     int32_t n_samples;
-    int32_t max_boxes_per_sample;    /* max over samples of the box count (sizes the smem cull masks)     */
+    int32_t max_boxes_per_sample;    /* max over samples of the box count (sizes the smem box tables)     */
+    int32_t n_boxes;                 /* total boxes in the batch (= sample_box_off[n_samples])            */
+    int32_t reserved_;
     const float* points;             /* [n_points_padded, 5] raw sweep rows                               */
     const int32_t* sample_sweep_off; /* [n_samples + 1] index into the sweep arrays                       */
     const uint32_t* sweep_start;     /* [n_sweeps] first point of the sweep (multiple of 4)               */
@@ -104,9 +106,10 @@ int msc_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_ma
  * Replaces: LiDARAgent._preprocess_point_cloud / _segment_ground (lidar_agent.py:103-132) and the raster
  * half of _generate_multi_layer_bev (:539-560) for batches, plus the [EXT] rows e1-e5 of SURVEY.md
  * section 8(a) (devkit from_file_multisweep, points_in_box, get_sample_data/view_points/box_in_image).
- * workspace: >= msc_fused_workspace_bytes() bytes, 16-byte aligned (holds the work counter).
+ * Two launches: a small table kernel (prepared boxes, projection, camera wedges, per-cell wedge classes -> workspace)
+ * and the streaming kernel.  workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned.
  */
-size_t msc_fused_workspace_bytes(int32_t n_samples);
+size_t msc_fused_workspace_bytes(const msc_params* params, int32_t n_samples, int32_t n_boxes);
 int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
                              void* workspace, size_t workspace_bytes, void* stream);
 

@@ -25,31 +25,27 @@
 
 namespace msc {
 
-// Launch shape: NT consumer threads + one producer warp.  A tile is NT*PPT points (20 B each).
-template <int NT, int PPT, int STAGES>
+// Launch shape: NT threads = NT/32 warps; every warp owns a private ring of STAGES tiles of 32*PPT points.
+template <int NT, int PPT, int STAGES, bool POSE_SMEM = false>
 struct Cfg {
-    static constexpr int kThreads = NT;            // consumer threads
-    static constexpr int kBlock = NT + 128;        // + one producer warpgroup (only its first warp issues TMA)
-    // setmaxnreg budgets: the producer warpgroup shrinks to 24 registers, the consumers take what that frees
-    static constexpr int kRegsLaunch = ((65536 / kBlock) / 8) * 8;
-    static constexpr int kRegsProducer = 24;
-    // consumers only take what the producer warpgroup released (never more: setmaxnreg.inc would spin forever)
-    static constexpr int kRegsConsumerRaw = kRegsLaunch + ((128 * (kRegsLaunch - kRegsProducer)) / NT / 8) * 8;
-    static constexpr int kRegsConsumer = kRegsConsumerRaw > 232 ? 232 : kRegsConsumerRaw;
-    static constexpr int kPtsPerThread = PPT;
-    static constexpr int kTilePts = NT * PPT;
-    static constexpr int kTileBytes = kTilePts * 20;
-    static constexpr int kStages = STAGES;
+    static constexpr bool kPoseInSmem = POSE_SMEM;  // pose rows read from smem per tile (64-register budgets)
+    static constexpr int kThreads = NT;
     static constexpr int kWarps = NT / 32;
-    static_assert(kTileBytes % 128 == 0, "tile stride keeps 128-byte alignment");
-    static_assert(STAGES <= 8, "Misc holds 8 barriers per kind");
+    static constexpr int kPtsPerThread = PPT;
+    static constexpr int kTilePts = 32 * PPT;          // points per warp tile
+    static constexpr int kTileBytes = kTilePts * 20;   // 1280 B for PPT = 2
+    static constexpr int kStages = STAGES;
+    static constexpr int kRingBytes = kWarps * STAGES * kTileBytes;
+    static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(STAGES >= 2 && STAGES <= 8, "ring depth");
 };
 constexpr int kMaxSweepsSmem = 64;  // per-sample sweep table cached in smem (larger samples read it from global)
 constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes the four LDS.128 conflict-free
 
 constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
 constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
-constexpr int kAccWords = 12;                 // per-box accumulators: count, min s, 3 x 3 limbs, pad
+constexpr int kAccWords = 8;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs
+constexpr int kMaxWarps = 32;
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
     int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, lut_off, misc_off, total_bytes;
@@ -63,7 +59,6 @@ struct FusedArgs {
     msc_batch_in in;
     msc_batch_out out;
     FusedLayout L;
-    uint32_t* work_counter;
     // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
     float two_r, resf, rcp_two_r, cscale, iscale;
     int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
@@ -71,12 +66,13 @@ struct FusedArgs {
 };
 
 struct Misc {  // small per-CTA state at misc_off
-    uint64_t full_bar[8];   // TMA bytes landed (producer -> consumers)
-    uint64_t empty_bar[8];  // every consumer warp is done with the stage (consumers -> producer)
+    uint64_t full_bar[kMaxWarps * 8];  // [warp][stage]: TMA bytes landed in that warp's ring slot
     float wedge[MSC_MAX_CAMS][6];
     uint32_t stats[MSC_STATS_STRIDE];
     uint32_t sweep_start[kMaxSweepsSmem], sweep_count[kMaxSweepsSmem];
     int32_t sample;
+    int32_t pad_[3];
+    double pose[kMaxSweepsSmem * 12];  // this sample's 3x4 sweep transforms (only used by POSE_SMEM shapes)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -115,109 +111,13 @@ __device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp
     return min(max(i, 0), res_m1);
 }
 
-// ------------------------------------------------------------------------------------------------ prologue
-// box preparation (global -> ego -> sensor, devkit points_in_box vectors, App. A.2) + cull rasterisation
-__device__ __noinline__ void prepare_box(const FusedArgs& A, const double* __restrict__ box, const double* __restrict__ ego,
-                                         const double* __restrict__ lcal, int b, float* __restrict__ boxp, uint2* __restrict__ cull) {
-    const msc_params& P = A.P;
-    const FusedLayout& L = A.L;
-    double c[3] = {box[0], box[1], box[2]};
-    double R[9];
-    quat_to_rot(box + 6, R);
-    frame_change(ego, c, R);
-    frame_change(lcal, c, R);
-    const double w = box[3], l = box[4], h = box[5];
-    const double hl = l / 2.0, hw = w / 2.0, hh = h / 2.0;
-    float* o = boxp + b * kBoxStride;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        o[r] = (float)(((R[r * 3 + 0] * hl + R[r * 3 + 1] * hw) + R[r * 3 + 2] * hh) + c[r]);
-        o[3 + r] = (float)(-(l * R[r * 3 + 0]));
-        o[6 + r] = (float)(-(w * R[r * 3 + 1]));
-        o[9 + r] = (float)(-(h * R[r * 3 + 2]));
-    }
-    o[12] = __fmaf_rn(o[5], o[5], __fmaf_rn(o[4], o[4], __fmul_rn(o[3], o[3])));
-    o[13] = __fmaf_rn(o[8], o[8], __fmaf_rn(o[7], o[7], __fmul_rn(o[6], o[6])));
-    o[14] = __fmaf_rn(o[11], o[11], __fmaf_rn(o[10], o[10], __fmul_rn(o[9], o[9])));
-    o[15] = 0.0f;
-    // Conservative oriented rasterisation of the xy footprint (a zonotope spanned by the projected edge
-    // vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the
-    // 2 mm margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
-    const float margin = 2e-3f;
-    const float cx = (float)c[0], cy = (float)c[1];
-    const float ex[3] = {o[3], o[6], o[9]}, ey[3] = {o[4], o[7], o[10]};
-    const float rx = 0.5f * (fabsf(ex[0]) + fabsf(ex[1]) + fabsf(ex[2])) + margin;
-    const float ry = 0.5f * (fabsf(ey[0]) + fabsf(ey[1]) + fabsf(ey[2])) + margin;
-    const int res_m1 = P.bev_res - 1;
-    const int cx0 = bev_cell<false>(cx - rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cx1 = bev_cell<false>(cx + rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cy0 = bev_cell<false>(cy - ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
-    const int last = L.cull_dim - 1;
-    for (int gy = cy0; gy <= cy1; ++gy) {
-        for (int gx = cx0; gx <= cx1; ++gx) {
-            // cell rectangle in metres (edge cells absorb everything clipped into them: treat them as unbounded
-            // by skipping the separating-axis rejection there)
-            bool reject = false;
-            if (gx > 0 && gx < last && gy > 0 && gy < last) {
-                const float mx = -P.bev_range + ((float)gx + 0.5f) * cell_m, my = -P.bev_range + ((float)gy + 0.5f) * cell_m;
-                const float dx = cx - mx, dy = cy - my;
-                const float hc = 0.5f * cell_m + margin;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    // axis = normal of projected edge k
-                    const float nx = -ey[k], ny = ex[k];
-                    const float nn = fabsf(nx) + fabsf(ny);
-                    if (nn > 1e-6f) {
-                        const float dist = fabsf(dx * nx + dy * ny);
-                        float rb = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) rb += 0.5f * fabsf(ex[j] * nx + ey[j] * ny);
-                        const float rc = hc * nn;
-                        if (dist > (rb + rc) * 1.0001f + margin * nn) reject = true;
-                    }
-                }
-            }
-            if (reject) continue;
-            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
-            for (;;) {
-                const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
-                if (old == kCullAll) break;
-                uint32_t nw = kCullAll;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (nw == kCullAll && ((old >> (8 * k)) & 0xffu) == 0xffu) nw = (old & ~(0xffu << (8 * k))) | ((uint32_t)b << (8 * k));
-                if (atomicCAS(slot, old, nw) == old) break;
-            }
-        }
-    }
-}
-
-// camera wedge for the FOV test: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W
-__device__ __noinline__ void prepare_wedge(const FusedArgs& A, const double* __restrict__ lcal, const double* __restrict__ ccal,
-                                           const double* __restrict__ K, float* __restrict__ wq) {
-    double Rl[9], Rc[9];
-    quat_to_rot(lcal + 3, Rl);
-    quat_to_rot(ccal + 3, Rc);
-    const double d0 = ccal[0] - lcal[0], d1 = ccal[1] - lcal[1], d2 = ccal[2] - lcal[2];
-    const double ox = (Rl[0] * d0 + Rl[3] * d1) + Rl[6] * d2;
-    const double oy = (Rl[1] * d0 + Rl[4] * d1) + Rl[7] * d2;
-    const double fx = K[0], cxp = K[2];
-    const double dl[3] = {(0.0 - cxp) / fx, 0.0, 1.0};
-    const double dr[3] = {((double)A.P.image_w - cxp) / fx, 0.0, 1.0};
-    double le[3], re[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        le[r] = (Rc[r * 3 + 0] * dl[0] + Rc[r * 3 + 1] * dl[1]) + Rc[r * 3 + 2] * dl[2];
-        re[r] = (Rc[r * 3 + 0] * dr[0] + Rc[r * 3 + 1] * dr[1]) + Rc[r * 3 + 2] * dr[2];
-    }
-    wq[0] = (float)ox; wq[1] = (float)oy;
-    wq[2] = (float)((Rl[0] * le[0] + Rl[3] * le[1]) + Rl[6] * le[2]);
-    wq[3] = (float)((Rl[1] * le[0] + Rl[4] * le[1]) + Rl[7] * le[2]);
-    wq[4] = (float)((Rl[0] * re[0] + Rl[3] * re[1]) + Rl[6] * re[2]);
-    wq[5] = (float)((Rl[1] * re[0] + Rl[4] * re[1]) + Rl[7] * re[2]);
-}
+// ------------------------------------------------------------------------------------------------ table kernel
+// Everything that does not touch points runs once per batch in a small, fully parallel kernel and lands in the
+// workspace: prepared boxes (devkit points_in_box vectors, App. A.2), box -> camera projection (A.3), camera
+// wedges, and the per-cull-cell wedge classes.  The streaming kernel then only copies its sample's rows to smem.
+struct TableLayout {  // offsets (bytes) into the workspace
+    size_t counter_off, boxprep_off, wedge_off, fovcls_off, total;
+};
 
 // exact wedge test (the definition): q = p - apex, cross(e_right, q) >= 0 and cross(q, e_left) >= 0
 __device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
@@ -245,189 +145,355 @@ __device__ __forceinline__ uint32_t classify_cell(const float* __restrict__ wq, 
     return 2u;                                          // straddling: run the exact test per point
 }
 
+// camera wedge: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W (f64, no FMA)
+__device__ void compute_wedge(int image_w, const double* __restrict__ lcal, const double* __restrict__ ccal, const double* __restrict__ K,
+                              float* __restrict__ wq) {
+    double Rl[9], Rc[9];
+    quat_to_rot(lcal + 3, Rl);
+    quat_to_rot(ccal + 3, Rc);
+    const double d0 = ccal[0] - lcal[0], d1 = ccal[1] - lcal[1], d2 = ccal[2] - lcal[2];
+    const double ox = (Rl[0] * d0 + Rl[3] * d1) + Rl[6] * d2;
+    const double oy = (Rl[1] * d0 + Rl[4] * d1) + Rl[7] * d2;
+    const double fx = K[0], cxp = K[2];
+    const double dl[3] = {(0.0 - cxp) / fx, 0.0, 1.0};
+    const double dr[3] = {((double)image_w - cxp) / fx, 0.0, 1.0};
+    double le[3], re[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        le[r] = (Rc[r * 3 + 0] * dl[0] + Rc[r * 3 + 1] * dl[1]) + Rc[r * 3 + 2] * dl[2];
+        re[r] = (Rc[r * 3 + 0] * dr[0] + Rc[r * 3 + 1] * dr[1]) + Rc[r * 3 + 2] * dr[2];
+    }
+    wq[0] = (float)ox; wq[1] = (float)oy;
+    wq[2] = (float)((Rl[0] * le[0] + Rl[3] * le[1]) + Rl[6] * le[2]);
+    wq[3] = (float)((Rl[1] * le[0] + Rl[4] * le[1]) + Rl[7] * le[2]);
+    wq[4] = (float)((Rl[0] * re[0] + Rl[3] * re[1]) + Rl[6] * re[2]);
+    wq[5] = (float)((Rl[1] * re[0] + Rl[4] * re[1]) + Rl[7] * re[2]);
+}
+
+// grid: ceil(max(n_boxes_total * max(n_cams,1), n_samples * cull_cells) / 256) blocks of 256 threads
+__global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
+                                                          unsigned char* __restrict__ ws) {
+    const msc_params& P = A.P;
+    const int n_cams = P.n_cams;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    float* const boxprep = reinterpret_cast<float*>(ws + T.boxprep_off);
+    float* const wedges = reinterpret_cast<float*>(ws + T.wedge_off);
+    uint16_t* const fovcls = reinterpret_cast<uint16_t*>(ws + T.fovcls_off);
+    // sample of a global box index: binary search in sample_box_off
+    auto sample_of_box = [&](int gb) {
+        int lo = 0, hi = A.in.n_samples;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.in.sample_box_off[mid] <= gb) lo = mid; else hi = mid; }
+        return lo;
+    };
+    // (1) prepared boxes: one thread per box
+    if (gid < n_boxes_total) {
+        const int sample = sample_of_box(gid);
+        const double* box = A.in.boxes + (size_t)gid * 10;
+        double c[3] = {box[0], box[1], box[2]};
+        double R[9];
+        quat_to_rot(box + 6, R);
+        frame_change(A.in.ego_pose + (size_t)sample * 7, c, R);
+        frame_change(A.in.lidar_calib + (size_t)sample * 7, c, R);
+        const double w = box[3], l = box[4], h = box[5];
+        const double hl = l / 2.0, hw = w / 2.0, hh = h / 2.0;
+        float* o = boxprep + (size_t)gid * kBoxStride;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            o[r] = (float)(((R[r * 3 + 0] * hl + R[r * 3 + 1] * hw) + R[r * 3 + 2] * hh) + c[r]);
+            o[3 + r] = (float)(-(l * R[r * 3 + 0]));
+            o[6 + r] = (float)(-(w * R[r * 3 + 1]));
+            o[9 + r] = (float)(-(h * R[r * 3 + 2]));
+        }
+        o[12] = __fmaf_rn(o[5], o[5], __fmaf_rn(o[4], o[4], __fmul_rn(o[3], o[3])));
+        o[13] = __fmaf_rn(o[8], o[8], __fmaf_rn(o[7], o[7], __fmul_rn(o[6], o[6])));
+        o[14] = __fmaf_rn(o[11], o[11], __fmaf_rn(o[10], o[10], __fmul_rn(o[9], o[9])));
+        o[15] = 0.0f;
+        o[16] = (float)c[0]; o[17] = (float)c[1]; o[18] = (float)c[2]; o[19] = 0.0f;  // centre, for the cull rasterisation
+    }
+    // (2) box -> camera projection (App. A.3): one thread per (box, camera)
+    if (n_cams > 0 && gid < n_boxes_total * n_cams) {
+        const int gb = gid / n_cams, c = gid - gb * n_cams;
+        const int sample = sample_of_box(gb);
+        project_box(A.in.boxes + (size_t)gb * 10, A.in.cam_ego_pose + ((size_t)sample * n_cams + c) * 7,
+                    A.in.cam_calib + ((size_t)sample * n_cams + c) * 7, A.in.cam_K + ((size_t)sample * n_cams + c) * 9, (double)P.image_w,
+                    (double)P.image_h, A.out.proj_visible + gid, A.out.proj_extent + (size_t)gid * 4);
+    }
+    // (3) wedge classes per (sample, cull cell); the wedge of every camera is recomputed per thread from the
+    //     sample's calibration (cheap next to one kernel-wide dependency)
+    const int ncc = A.L.cull_dim * A.L.cull_dim;
+    if (n_cams > 0 && gid < A.in.n_samples * ncc) {
+        const int sample = gid / ncc, i = gid - sample * ncc;
+        const int gy = i / A.L.cull_dim, gx = i - gy * A.L.cull_dim;
+        const float cell_m = (A.two_r / A.resf) * (float)(1 << A.L.cull_shift);
+        const int last = A.L.cull_dim - 1;
+        const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
+        // edge cells absorb everything clipped into them
+        const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
+        const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
+        const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
+        const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
+        uint32_t bits = 0;
+        for (int c = 0; c < n_cams; ++c) {
+            float wq[6];
+            compute_wedge(P.image_w, A.in.lidar_calib + (size_t)sample * 7, A.in.cam_calib + ((size_t)sample * n_cams + c) * 7,
+                          A.in.cam_K + ((size_t)sample * n_cams + c) * 9, wq);
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) wedges[((size_t)sample * MSC_MAX_CAMS + c) * 6 + k] = wq[k];
+            }
+            const uint32_t k = classify_cell(wq, x0, x1, y0, y1);
+            bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
+        }
+        fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ streaming kernel
+// Conservative oriented rasterisation of a prepared box's xy footprint (a zonotope spanned by the projected edge
+// vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the 2 mm
+// margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
+__device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint2* __restrict__ cull) {
+    const msc_params& P = A.P;
+    const FusedLayout& L = A.L;
+    const float margin = 2e-3f;
+    const float cx = o[16], cy = o[17];
+    const float ex[3] = {o[3], o[6], o[9]}, ey[3] = {o[4], o[7], o[10]};
+    const float rx = 0.5f * (fabsf(ex[0]) + fabsf(ex[1]) + fabsf(ex[2])) + margin;
+    const float ry = 0.5f * (fabsf(ey[0]) + fabsf(ey[1]) + fabsf(ey[2])) + margin;
+    const int res_m1 = P.bev_res - 1;
+    const int cx0 = bev_cell<false>(cx - rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cx1 = bev_cell<false>(cx + rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy0 = bev_cell<false>(cy - ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
+    const int last = L.cull_dim - 1;
+    for (int gy = cy0; gy <= cy1; ++gy) {
+        for (int gx = cx0; gx <= cx1; ++gx) {
+            // edge cells absorb everything clipped into them: never reject those
+            bool reject = false;
+            if (gx > 0 && gx < last && gy > 0 && gy < last) {
+                const float mx = -P.bev_range + ((float)gx + 0.5f) * cell_m, my = -P.bev_range + ((float)gy + 0.5f) * cell_m;
+                const float dx = cx - mx, dy = cy - my;
+                const float hc = 0.5f * cell_m + margin;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float nx = -ey[k], ny = ex[k];  // normal of projected edge k
+                    const float nn = fabsf(nx) + fabsf(ny);
+                    if (nn > 1e-6f) {
+                        const float dist = fabsf(dx * nx + dy * ny);
+                        float rb = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) rb += 0.5f * fabsf(ex[j] * nx + ey[j] * ny);
+                        if (dist > (rb + hc * nn) * 1.0001f + margin * nn) reject = true;
+                    }
+                }
+            }
+            if (reject) continue;
+            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
+            for (;;) {
+                const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
+                if (old == kCullAll) break;
+                uint32_t nw = kCullAll;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (nw == kCullAll && ((old >> (8 * k)) & 0xffu) == 0xffu) nw = (old & ~(0xffu << (8 * k))) | ((uint32_t)b << (8 * k));
+                if (atomicCAS(slot, old, nw) == old) break;
+            }
+        }
+    }
+}
+
+// A.2 exact membership test of one point against one prepared box + accumulator update.
+// Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis (each a fire-and-forget ATOMS).
+__device__ __forceinline__ void box_test_accumulate(const FusedArgs& A, const float* __restrict__ boxp, uint32_t* __restrict__ boxacc, int b,
+                                                    float xr, float yr, float zr, float s2) {
+    const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
+    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+    const float v0 = __fsub_rn(xr, b0.x), v1 = __fsub_rn(yr, b0.y), v2 = __fsub_rn(zr, b0.z);
+    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
+    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
+    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
+    if (iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z && !(A.debug_skip & 8u)) {
+        uint32_t* acc = boxacc + b * kAccWords;
+        atomicAdd(acc + 0, 1u);
+        atomicMin(acc + 1, __float_as_uint(s2));
+        const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
+        const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
+        const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
+        atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
+        atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
+        atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
+    }
+}
+
 template <class C, bool FOV, bool FASTDIV>
-__global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __grid_constant__ FusedArgs A) {
-    constexpr int NT = C::kThreads, S = C::kStages, TP = C::kTilePts, PPT = C::kPtsPerThread;
+__global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
+                                                                       unsigned char* __restrict__ ws) {
+    constexpr int NT = C::kThreads, S = C::kStages, TP = C::kTilePts, PPT = C::kPtsPerThread, W = C::kWarps;
+    constexpr bool MSMEM = C::kPoseInSmem;
     extern __shared__ __align__(128) unsigned char smem[];
     const msc_params& P = A.P;
     const FusedLayout& L = A.L;
-    float* const tiles = reinterpret_cast<float*>(smem + L.tiles_off);
     uint2* const window = reinterpret_cast<uint2*>(smem + L.window_off);
     uint2* const cull = reinterpret_cast<uint2*>(smem + L.cull_off);            // .x box ids, .y wedge classes
     float* const boxp = reinterpret_cast<float*>(smem + L.boxp_off);            // [max_boxes][kBoxStride]
     uint32_t* const boxacc = reinterpret_cast<uint32_t*>(smem + L.boxacc_off);  // [max_boxes][kAccWords]
     Misc* const misc = reinterpret_cast<Misc*>(smem + L.misc_off);
+    uint32_t* const work_counter = reinterpret_cast<uint32_t*>(ws + T.counter_off);
+    const float* const g_boxprep = reinterpret_cast<const float*>(ws + T.boxprep_off);
+    const float* const g_wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
+    const uint16_t* const g_fovcls = reinterpret_cast<const uint16_t*>(ws + T.fovcls_off);
 
-    const int tid = threadIdx.x, lane = threadIdx.x & 31;
-    const bool is_producer = tid >= NT;  // the last warpgroup only feeds the TMA ring (its first warp)
+    const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* const ring = reinterpret_cast<float*>(smem + L.tiles_off) + (size_t)warp * S * (C::kTileBytes / 4);  // this warp's slots
+    uint64_t* const full = misc->full_bar + warp * 8;
     const int res = P.bev_res, res_m1 = P.bev_res - 1;
     const size_t ncell = (size_t)res * (size_t)res;
     const int n_cams = P.n_cams;
+    const uint64_t policy = l2_policy_evict_first();
 
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&misc->full_bar[s], 1); mbar_init(&misc->empty_bar[s], C::kWarps); }
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
+    uint32_t wk = 0;  // tiles this warp has consumed since launch (ring position and mbarrier parity)
     __syncthreads();
-    constexpr int kBlock = C::kBlock;
-    auto block_sync = [] { asm volatile("bar.sync 0, %0;" ::"n"(kBlock) : "memory"); };  // all roles, from either code path
 
-    if (is_producer) {
-        // ============================================================== TMA producer warpgroup
-        reg_dealloc<C::kRegsProducer>();
-        const uint64_t policy = l2_policy_evict_first();
-        uint32_t g = 0;  // tiles requested since launch (ring position and mbarrier parity)
-        for (;;) {
-            if (tid == NT) misc->sample = (int32_t)atomicAdd(A.work_counter, 1u);
-            block_sync();  // (1) sample id published
-            const int sample = misc->sample;
-            block_sync();  // (2) everyone has read it
-            if (sample >= A.in.n_samples) break;
-            if (tid >= NT + 32) continue;  // idle warps of the producer warpgroup
-            const int sw0 = A.in.sample_sweep_off[sample], sw1 = A.in.sample_sweep_off[sample + 1];
-            for (int s = sw0; s < sw1; ++s) {
-                const uint32_t cnt = A.in.sweep_count[s];
-                const float* base = A.in.points + (size_t)A.in.sweep_start[s] * 5;
-                for (uint32_t first = 0; first < cnt; first += TP, ++g) {
-                    if (lane == 0) {
-                        const int stage = (int)(g % S);
-                        const uint32_t use = g / S;
-                        if (use >= 1) mbar_wait_parity(&misc->empty_bar[stage], (use - 1) & 1u);  // consumers released the slot
-                        const uint32_t npts = min((uint32_t)TP, cnt - first);
-                        const uint32_t bytes = (npts * 20u + 15u) & ~15u;
-                        mbar_arrive_expect_tx(&misc->full_bar[stage], bytes);
-                        bulk_load(tiles + (size_t)stage * (C::kTileBytes / 4), base + (size_t)first * 5, bytes, &misc->full_bar[stage], policy);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        return;
-    }
-
-    // ================================================================== consumer warpgroups
-    reg_alloc<C::kRegsConsumer>();
-    uint32_t gk = 0;  // tiles consumed since launch (ring position and mbarrier parity)
     for (;;) {
-        block_sync();  // (1)
+        // ------------------------------------------------------------ fetch a sample
+        if (tid == 0) misc->sample = (int32_t)atomicAdd(work_counter, 1u);
+        __syncthreads();
         const int sample = misc->sample;
-        block_sync();  // (2)
         if (sample >= A.in.n_samples) break;
-        const int sw0 = A.in.sample_sweep_off[sample], sw1 = A.in.sample_sweep_off[sample + 1];
-        uint32_t total_tiles = 0, n_in = 0;
-        for (int s = sw0; s < sw1; ++s) {
-            const uint32_t c = A.in.sweep_count[s];
-            total_tiles += (c + TP - 1) / TP;
-            n_in += c;
-        }
 
-        // -------------------------------------------------------------- consumers
+        const int sw0 = A.in.sample_sweep_off[sample], sw1 = A.in.sample_sweep_off[sample + 1];
+        const int n_sw = sw1 - sw0;
+        if (tid < kMaxSweepsSmem && tid < n_sw) {
+            misc->sweep_start[tid] = A.in.sweep_start[sw0 + tid];
+            misc->sweep_count[tid] = A.in.sweep_count[sw0 + tid];
+        }
+        if (MSMEM) {
+            for (int i = tid; i < min(n_sw, kMaxSweepsSmem) * 12; i += NT) misc->pose[i] = A.in.sweep_pose[(size_t)sw0 * 12 + i];
+        }
+        if (tid < MSC_STATS_STRIDE) misc->stats[tid] = 0u;
+        __syncthreads();
+        auto sweep_cnt = [&](int si) -> uint32_t { return si < kMaxSweepsSmem ? misc->sweep_count[si] : A.in.sweep_count[sw0 + si]; };
+        auto sweep_beg = [&](int si) -> uint32_t { return si < kMaxSweepsSmem ? misc->sweep_start[si] : A.in.sweep_start[sw0 + si]; };
+
+        // Warp `warp` owns tiles warp, warp + W, warp + 2W, ... of every sweep.  Two cursors walk that sequence:
+        // p_* for the refills (S - 1 tiles ahead) and c_* for consumption; both cache their sweep's size and base.
+        int p_si = -1, c_si = -1;
+        uint32_t p_first = 0, p_cnt = 0, p_base = 0, c_first = 0, c_cnt = 0, p_issued = 0;
+        const uint32_t wk0 = wk;
+        auto issue_next = [&]() {  // whole warp (uniform control flow); lane 0 talks to the TMA unit
+            while (p_first >= p_cnt) {  // next sweep that still has a tile for this warp
+                if (++p_si >= n_sw) { p_si = n_sw; p_cnt = 0; p_first = 0; return; }
+                p_cnt = sweep_cnt(p_si); p_base = sweep_beg(p_si); p_first = (uint32_t)warp * TP;
+            }
+            const uint32_t npts = min((uint32_t)TP, p_cnt - p_first);
+            const int stage = (int)((wk0 + p_issued) % S);
+            if (lane == 0) {
+                const uint32_t bytes = (npts * 20u + 15u) & ~15u;
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                bulk_load(ring + (size_t)stage * (C::kTileBytes / 4), A.in.points + ((size_t)p_base + p_first) * 5, bytes, &full[stage], policy);
+            }
+            p_first += W * TP;
+            ++p_issued;
+        };
+#pragma unroll 1
+        for (int s = 0; s < S - 1; ++s) issue_next();  // these loads overlap the prologue below
+
+        // ------------------------------------------------------------ prologue: zero accumulators, copy tables to smem
         const int bx0 = A.in.sample_box_off[sample];
         int n_boxes = A.in.sample_box_off[sample + 1] - bx0;
         const bool box_overflow = n_boxes > L.max_boxes;  // caller under-declared max_boxes_per_sample
         if (box_overflow) n_boxes = L.max_boxes;
         uint32_t* const g_ci = A.out.bev_ci + (size_t)sample * ncell * 2;
         float* const g_h = A.out.bev_height + (size_t)sample * ncell;
-        const double* const ego = A.in.ego_pose + (size_t)sample * 7;
-        const double* const lcal = A.in.lidar_calib + (size_t)sample * 7;
         {
             uint4* w4 = reinterpret_cast<uint4*>(window);
             const int n_w4 = (L.win_w * L.win_w * 8) / 16;
             for (int i = tid; i < n_w4; i += NT) w4[i] = make_uint4(0, 0, 0, 0);
             const int n_cull = L.cull_dim * L.cull_dim;
-            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(kCullEmpty, 0u);
+            const uint16_t* fc = g_fovcls + (size_t)sample * n_cull;
+            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(kCullEmpty, (FOV && n_cams > 0) ? (uint32_t)fc[i] : 0u);
             for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
-            if (tid < MSC_STATS_STRIDE) misc->stats[tid] = 0u;
-            if (tid < kMaxSweepsSmem && sw0 + tid < sw1) {
-                misc->sweep_start[tid] = A.in.sweep_start[sw0 + tid];
-                misc->sweep_count[tid] = A.in.sweep_count[sw0 + tid];
-            }
+            const float4* bsrc = reinterpret_cast<const float4*>(g_boxprep + (size_t)bx0 * kBoxStride);
+            for (int i = tid; i < n_boxes * (kBoxStride / 4); i += NT) reinterpret_cast<float4*>(boxp)[i] = bsrc[i];
+            if (FOV && tid < n_cams * 6) misc->wedge[tid / 6][tid % 6] = g_wedges[((size_t)sample * MSC_MAX_CAMS + tid / 6) * 6 + tid % 6];
             // zero-fill this sample's global layers (window cells are overwritten by the flush; filling them too
             // keeps the stores fully coalesced)
             uint4* c4 = reinterpret_cast<uint4*>(g_ci);
             for (size_t i = tid; i < ncell / 2; i += NT) c4[i] = make_uint4(0, 0, 0, 0);
             uint4* h4 = reinterpret_cast<uint4*>(g_h);
             for (size_t i = tid; i < ncell / 4; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
-            if (FOV && tid < n_cams)
-                prepare_wedge(A, lcal, A.in.cam_calib + ((size_t)sample * n_cams + tid) * 7, A.in.cam_K + ((size_t)sample * n_cams + tid) * 9,
-                              misc->wedge[tid]);
         }
         __threadfence();
-        consumer_sync<NT>();
-        {
-            for (int b = tid; b < n_boxes; b += NT) prepare_box(A, A.in.boxes + (size_t)(bx0 + b) * 10, ego, lcal, b, boxp, cull);
-            if (FOV) {
-                // per cull cell: which cameras contain the whole cell (bits 0-7) and which need the exact test (8-15)
-                const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
-                const int last = L.cull_dim - 1;
-                const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
-                for (int i = tid; i < L.cull_dim * L.cull_dim; i += NT) {
-                    const int gy = i / L.cull_dim, gx = i - gy * L.cull_dim;
-                    // edge cells absorb everything clipped into them
-                    const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
-                    const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
-                    const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
-                    const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
-                    uint32_t bits = 0;
-                    for (int c = 0; c < n_cams; ++c) {
-                        const uint32_t k = classify_cell(misc->wedge[c], x0, x1, y0, y1);
-                        bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
-                    }
-                    cull[i].y = bits;
-                }
-            }
-            // box -> camera projection (App. A.3), one (box, camera) pair per thread
-            const double Wd = (double)P.image_w, Hd = (double)P.image_h;
-            for (int t = tid; t < n_boxes * n_cams; t += NT) {
-                const int b = t / n_cams, c = t - b * n_cams;
-                const size_t o = (size_t)(bx0 + b) * n_cams + c;
-                project_box(A.in.boxes + (size_t)(bx0 + b) * 10, A.in.cam_ego_pose + ((size_t)sample * n_cams + c) * 7,
-                            A.in.cam_calib + ((size_t)sample * n_cams + c) * 7, A.in.cam_K + ((size_t)sample * n_cams + c) * 9, Wd,
-                            Hd, A.out.proj_visible + o, A.out.proj_extent + o * 4);
-            }
-        }
-        consumer_sync<NT>();
+        __syncthreads();
+        for (int b = tid; b < n_boxes; b += NT) rasterise_box(A, boxp + b * kBoxStride, b, cull);
+        __syncthreads();
 
-        // ------------------------------------------------------------ main loop over tiles (no CTA-wide barrier)
+        // ------------------------------------------------------------ main loop: this warp's tiles, no cross-warp sync
         uint32_t c_close = 0, c_kept = 0, c_ground = 0;  // per-thread counters (flushed once per sample)
         uint32_t cam_lo = 0, cam_hi = 0;                 // eight 8-bit per-camera counters, spilled every <= 255 points
         uint32_t cam_pts = 0;
-
-        int c_sweep = 0;  // index into this sample's sweeps
-        uint32_t c_first = 0;
-        uint32_t cur_cnt = 0;
-        double M[12];
-        bool have_pose = false;
-        auto sweep_cnt = [&](int si) -> uint32_t { return si < kMaxSweepsSmem ? misc->sweep_count[si] : A.in.sweep_count[sw0 + si]; };
-        cur_cnt = (sw1 > sw0) ? sweep_cnt(0) : 0u;
-        for (uint32_t k = 0; k < total_tiles; ++k) {
-            while (c_first >= cur_cnt) { ++c_sweep; c_first = 0; cur_cnt = sweep_cnt(c_sweep); have_pose = false; }
-            if (!have_pose) {
-                ld_pose(A.in.sweep_pose + (size_t)(sw0 + c_sweep) * 12, M);
-                have_pose = true;
+        double M[MSMEM ? 1 : 12];
+        const double* Ms = nullptr;
+        for (;;) {
+            issue_next();  // refill the slot consumed in the previous iteration (S - 1 tiles ahead)
+            bool done = false;
+            while (c_first >= c_cnt) {
+                if (++c_si >= n_sw) { done = true; break; }
+                c_cnt = sweep_cnt(c_si); c_first = (uint32_t)warp * TP;
+                if (c_first < c_cnt) {
+                    if (MSMEM) Ms = (c_si < kMaxSweepsSmem) ? (misc->pose + c_si * 12) : (A.in.sweep_pose + (size_t)(sw0 + c_si) * 12);
+                    else ld_pose(A.in.sweep_pose + (size_t)(sw0 + c_si) * 12, M);
+                }
             }
-            const uint32_t npts = min((uint32_t)TP, cur_cnt - c_first);
-            const int stage = (int)(gk % S);
-            mbar_wait_parity(&misc->full_bar[stage], (gk / S) & 1u);
-            const float* tp = tiles + (size_t)stage * (C::kTileBytes / 4) + tid * 5;
+            if (done) break;
+            const uint32_t npts = min((uint32_t)TP, c_cnt - c_first);
+            const int stage = (int)(wk % S);
+            mbar_wait_parity(&full[stage], (wk / S) & 1u);
+            const float* tp = ring + (size_t)stage * (C::kTileBytes / 4) + lane * 5;
 
-            // ---- phase A: branch-free over the thread's PPT points so their dependency chains interleave
+            // ---- phase A: branch-free over the lane's PPT points so their dependency chains interleave
             float xr[PPT], yr[PPT], zr[PPT], s2[PPT], inten[PPT];
             int ix[PPT], iy[PPT];
             uint2 ce[PPT];
-            bool alive[PPT], keep[PPT];
+            bool keep[PPT], alive[PPT];
+            double xd[PPT], yd[PPT], zd[PPT];
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
-                const bool valid = (uint32_t)tid + (uint32_t)u * NT < npts;
-                const float x = tp[u * NT * 5 + 0], y = tp[u * NT * 5 + 1], z = tp[u * NT * 5 + 2];
-                inten[u] = tp[u * NT * 5 + 3];
+                const bool valid = (uint32_t)lane + (uint32_t)u * 32u < npts;
+                const float x = tp[u * 160 + 0], y = tp[u * 160 + 1], z = tp[u * 160 + 2];
+                inten[u] = tp[u * 160 + 3];
                 // A.1 remove_close (square, sweep's own sensor frame)
                 alive[u] = valid && !(fabsf(x) < P.remove_close_radius && fabsf(y) < P.remove_close_radius);
-                // A.1 f64 matrix x f32 point -> f32
-                const double xd = (double)x, yd = (double)y, zd = (double)z;
-                xr[u] = (float)__fma_rn(M[0], xd, __fma_rn(M[1], yd, __fma_rn(M[2], zd, M[3])));
-                yr[u] = (float)__fma_rn(M[4], xd, __fma_rn(M[5], yd, __fma_rn(M[6], zd, M[7])));
-                zr[u] = (float)__fma_rn(M[8], xd, __fma_rn(M[9], yd, __fma_rn(M[10], zd, M[11])));
+                xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
+                c_close += alive[u] ? 1u : 0u;
+            }
+            __syncwarp();  // every lane has read its rows: the slot may be refilled at the top of the next iteration
+            // A.1 f64 matrix x f32 point -> f32, one matrix row at a time (keeps few pose values live when they come from smem)
+            if (MSMEM) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double2 m01 = *reinterpret_cast<const double2*>(Ms + r * 4), m23 = *reinterpret_cast<const double2*>(Ms + r * 4 + 2);
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        const float v = (float)__fma_rn(m01.x, xd[u], __fma_rn(m01.y, yd[u], __fma_rn(m23.x, zd[u], m23.y)));
+                        if (r == 0) xr[u] = v; else if (r == 1) yr[u] = v; else zr[u] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    xr[u] = (float)__fma_rn(M[0], xd[u], __fma_rn(M[1], yd[u], __fma_rn(M[2], zd[u], M[3])));
+                    yr[u] = (float)__fma_rn(M[MSMEM ? 0 : 4], xd[u], __fma_rn(M[MSMEM ? 0 : 5], yd[u], __fma_rn(M[MSMEM ? 0 : 6], zd[u], M[MSMEM ? 0 : 7])));
+                    zr[u] = (float)__fma_rn(M[MSMEM ? 0 : 8], xd[u], __fma_rn(M[MSMEM ? 0 : 9], yd[u], __fma_rn(M[MSMEM ? 0 : 10], zd[u], M[MSMEM ? 0 : 11])));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
                 // lidar_agent.py:106-110, sqrt-free (thresholds on s are exact, geometry.sqrt_thresholds)
                 s2[u] = __fadd_rn(__fmul_rn(xr[u], xr[u]), __fmul_rn(yr[u], yr[u]));
                 keep[u] = alive[u] && (s2[u] >= P.s_lo) && (s2[u] <= P.s_hi) && (zr[u] < P.z_max) && (zr[u] > P.z_min);
@@ -435,7 +501,6 @@ __global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __gr
                 ix[u] = bev_cell<FASTDIV>(xr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
                 iy[u] = bev_cell<FASTDIV>(yr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
                 ce[u] = cull[(iy[u] >> L.cull_shift) * L.cull_dim + (ix[u] >> L.cull_shift)];
-                c_close += alive[u] ? 1u : 0u;
             }
             // ---- phase B: data-dependent work per kept point
 #pragma unroll
@@ -474,42 +539,17 @@ __global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __gr
                 // A.2 oriented-box membership for the candidate boxes of this cull cell
                 uint32_t ids = ce[u].x;
                 if (ids == kCullEmpty || (A.debug_skip & 2u)) continue;
-                int b_all = (ids == kCullAll) ? 0 : -1;  // >= 0: crowded cell, test every box
-                for (;;) {
-                    int b;
-                    if (b_all >= 0) {
-                        if (b_all >= n_boxes) break;
-                        b = b_all++;
-                    } else {
-                        b = (int)(ids & 0xffu);
-                        if (b == 0xff) break;
-                        ids = (ids >> 8) | 0xff000000u;
-                    }
-                    const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
-                    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-                    const float v0 = __fsub_rn(xr[u], b0.x), v1 = __fsub_rn(yr[u], b0.y), v2 = __fsub_rn(zr[u], b0.z);
-                    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
-                    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
-                    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
-                    if (iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z && !(A.debug_skip & 8u)) {
-                        uint32_t* acc = boxacc + b * kAccWords;
-                        atomicAdd(acc + 0, 1u);
-                        atomicMin(acc + 1, __float_as_uint(s2[u]));
-                        // fixed-point centroid sums: non-negative biased value split into three 9-bit limbs
-                        const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr[u], A.cscale)) + A.centroid_bias);
-                        const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr[u], A.cscale)) + A.centroid_bias);
-                        const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr[u], A.cscale)) + A.centroid_bias);
-                        atomicAdd(acc + 2, qx & 511u); atomicAdd(acc + 3, (qx >> 9) & 511u); atomicAdd(acc + 4, qx >> 18);
-                        atomicAdd(acc + 5, qy & 511u); atomicAdd(acc + 6, (qy >> 9) & 511u); atomicAdd(acc + 7, qy >> 18);
-                        atomicAdd(acc + 8, qz & 511u); atomicAdd(acc + 9, (qz >> 9) & 511u); atomicAdd(acc + 10, qz >> 18);
-                    }
+                if (ids == kCullAll) {  // crowded cell (more than four boxes): test every box
+                    for (int b = 0; b < n_boxes; ++b) box_test_accumulate(A, boxp, boxacc, b, xr[u], yr[u], zr[u], s2[u]);
+                    continue;
                 }
+                do {
+                    box_test_accumulate(A, boxp, boxacc, (int)(ids & 0xffu), xr[u], yr[u], zr[u], s2[u]);
+                    ids = (ids >> 8) | 0xff000000u;
+                } while ((ids & 0xffu) != 0xffu);
             }
-            // release the stage to the producer: one arrival per consumer warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&misc->empty_bar[stage]);
-            ++gk;
-            c_first += TP;
+            ++wk;
+            c_first += W * TP;
             if (FOV) {
                 cam_pts += PPT;
                 if (cam_pts > 255u - PPT) {  // spill the byte counters before any of them can wrap
@@ -535,7 +575,7 @@ __global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __gr
                 if (lane == 0 && r) atomicAdd(&misc->stats[i < 3 ? 1 + i : 2 + i], r);
             }
         }
-        consumer_sync<NT>();  // every tile of the sample is accumulated
+        __syncthreads();  // every tile of the sample is accumulated
         {
             // window flush: coalesced 16-byte stores of (count, isum) pairs, two cells per store
             const int half_w = L.win_w >> 1;  // win_w and win_lo are even -> 16-byte aligned rows
@@ -547,13 +587,13 @@ __global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __gr
                 *reinterpret_cast<uint4*>(g_ci + cell * 2) = v;
                 flags |= (v.x >= 65536u || v.z >= 65536u) ? 1u : 0u;
             }
-            if (flags) atomicOr(&misc->stats[13], flags);
             // per-box results
             for (int b = tid; b < n_boxes; b += NT) {
                 const uint32_t* acc = boxacc + b * kAccWords;
                 const uint32_t cnt = acc[0];
                 const size_t o = (size_t)(bx0 + b);
                 A.out.box_count[o] = cnt;
+                if (cnt >= (1u << 20)) flags |= 2u;  // 12-bit limb sums may have wrapped
                 if (cnt == 0) {
                     A.out.box_nearest[o] = INFINITY;
                     A.out.box_centroid[o * 3 + 0] = 0.0f; A.out.box_centroid[o * 3 + 1] = 0.0f; A.out.box_centroid[o * 3 + 2] = 0.0f;
@@ -562,23 +602,26 @@ __global__ void __launch_bounds__(C::kBlock, 1) fused_evidence_kernel(const __gr
                     const double den = (double)cnt * (double)A.cscale;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const unsigned long long biased = (unsigned long long)acc[2 + 3 * k] + ((unsigned long long)acc[3 + 3 * k] << 9) +
-                                                          ((unsigned long long)acc[4 + 3 * k] << 18);
+                        const unsigned long long biased = (unsigned long long)acc[2 + 2 * k] + ((unsigned long long)acc[3 + 2 * k] << 12);
                         const long long sum = (long long)biased - (long long)cnt * (long long)A.centroid_bias;
                         A.out.box_centroid[o * 3 + k] = (float)((double)sum / den);
                     }
                 }
             }
+            if (flags) atomicOr(&misc->stats[13], flags);
         }
-        consumer_sync<NT>();
+        __syncthreads();
         if (tid < MSC_STATS_STRIDE) {
             uint32_t v = misc->stats[tid];
-            if (tid == 0) v = n_in;
+            if (tid == 0) {
+                v = 0;
+                for (int s = sw0; s < sw1; ++s) v += A.in.sweep_count[s];
+            }
             if (tid == 4) v = misc->stats[2] - misc->stats[3];  // n_object = n_kept - n_ground
             if (tid == 13 && box_overflow) v |= 0x80000000u;
             A.out.stats[(size_t)sample * MSC_STATS_STRIDE + tid] = v;
         }
-        // (block_sync (1) at the top of the loop orders these reads before the next sample re-zeroes the smem)
+        // (the __syncthreads after the next sample fetch orders these reads before the smem is re-zeroed)
     }
 }
 
@@ -589,9 +632,9 @@ static int g_opt_fov = 1;
 static int g_opt_window = 0;       // 0 = auto (largest that fits)
 static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
 static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
-static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 static int g_opt_debug_skip = 0;
-static int g_opt_config = 0;       // launch shape: 0 = 512 thr x 2 pts, 4 stages; 1 = 512x2, 3 stages; 2 = 384x2, 5 stages
+static int g_opt_config = 0;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem
+static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 
 // divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
 static bool fastdiv_verified(float two_r) {
@@ -602,17 +645,35 @@ static bool fastdiv_verified(float two_r) {
     return frexpf(two_r, &e) == 0.5f;  // powers of two divide exactly either way
 }
 
-static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int stage_bytes, FusedLayout* L) {
-    const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
+static void cull_geometry(const msc_params& P, int* shift, int* dim) {
     const float cell_m = 2.0f * P.bev_range / (float)P.bev_res;
-    int shift = 0;
-    if (g_opt_cull_shift >= 0) shift = g_opt_cull_shift;
-    else while ((float)(1 << (shift + 1)) * cell_m <= 2.0f + 1e-6f && shift < 10) ++shift;
-    L->cull_shift = shift;
-    L->cull_dim = ((P.bev_res - 1) >> shift) + 1;
+    int sh = 0;
+    if (g_opt_cull_shift >= 0) sh = g_opt_cull_shift;
+    else while ((float)(1 << (sh + 1)) * cell_m <= 2.0f + 1e-6f && sh < 10) ++sh;
+    *shift = sh;
+    *dim = ((P.bev_res - 1) >> sh) + 1;
+}
+
+static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes) {
+    int shift, dim;
+    cull_geometry(P, &shift, &dim);
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    TableLayout T;
+    size_t off = 0;
+    T.counter_off = off; off = align(off + 256);
+    T.boxprep_off = off; off = align(off + (size_t)(n_boxes > 0 ? n_boxes : 1) * kBoxStride * 4);
+    T.wedge_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * MSC_MAX_CAMS * 6 * 4);
+    T.fovcls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 2);
+    T.total = off;
+    return T;
+}
+
+static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, FusedLayout* L) {
+    const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
+    cull_geometry(P, &L->cull_shift, &L->cull_dim);
     L->max_boxes = cap;
     int off = 0;
-    L->tiles_off = off; off += stage_bytes;
+    L->tiles_off = off; off += ring_bytes; off = (off + 127) & ~127;
     L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
@@ -633,33 +694,43 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
 }
 
 template <class C, bool FOV, bool FASTDIV>
-static int launch_fused(const FusedArgs& args, int grid, cudaStream_t stream) {
+static int launch_fused(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream) {
     auto kern = fused_evidence_kernel<C, FOV, FASTDIV>;
     MSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, args.L.total_bytes));
-    kern<<<grid, C::kBlock, args.L.total_bytes, stream>>>(args);
+    kern<<<grid, C::kThreads, args.L.total_bytes, stream>>>(args, T, ws);
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
 }
 template <class C>
-static int dispatch_fused(FusedArgs& args, const msc_params& P, int max_boxes, int smem_optin, int grid, bool fov, bool fast, cudaStream_t stream) {
-    if (compute_layout(P, max_boxes, smem_optin, C::kStages * C::kTileBytes, &args.L) != 0) {
+static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid, bool fov,
+                          bool fast, cudaStream_t stream) {
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, &args.L) != 0) {
         set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
         return MSC_ERR_UNSUPPORTED;
     }
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
-    if (fov) return fast ? launch_fused<C, true, true>(args, grid, stream) : launch_fused<C, true, false>(args, grid, stream);
-    return fast ? launch_fused<C, false, true>(args, grid, stream) : launch_fused<C, false, false>(args, grid, stream);
+    // (1) tables: prepared boxes, projection, wedges, wedge classes
+    const int ncc = args.L.cull_dim * args.L.cull_dim;
+    long long work = (long long)n_boxes_total * (args.P.n_cams > 0 ? args.P.n_cams : 1);
+    if ((long long)args.in.n_samples * ncc > work) work = (long long)args.in.n_samples * ncc;
+    if (work > 0) {
+        fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
+        MSC_CUDA(cudaGetLastError());
+    }
+    // (2) the streaming pass
+    if (fov) return fast ? launch_fused<C, true, true>(args, T, ws, grid, stream) : launch_fused<C, true, false>(args, T, ws, grid, stream);
+    return fast ? launch_fused<C, false, true>(args, T, ws, grid, stream) : launch_fused<C, false, false>(args, T, ws, grid, stream);
 }
 
 }  // namespace msc
 
 extern "C" {
 
-size_t msc_fused_workspace_bytes(int32_t n_samples) {
-    (void)n_samples;
-    return 256;
+size_t msc_fused_workspace_bytes(const msc_params* params, int32_t n_samples, int32_t n_boxes) {
+    if (!params) return 0;
+    return msc::table_layout(*params, n_samples, n_boxes).total;
 }
 
 int msc_fused_set_option(const char* key, int32_t value) {
@@ -680,10 +751,10 @@ int msc_fused_get_option(const char* key, int32_t* value) {
     if (!strcmp(key, "window")) { *value = msc::g_opt_window; return MSC_OK; }
     if (!strcmp(key, "cull_shift")) { *value = msc::g_opt_cull_shift; return MSC_OK; }
     if (!strcmp(key, "fastdiv")) { *value = msc::g_opt_fastdiv; return MSC_OK; }
+    if (!strcmp(key, "config")) { *value = msc::g_opt_config; return MSC_OK; }
     if (!strcmp(key, "last_window")) { *value = msc::g_last_window; return MSC_OK; }
     if (!strcmp(key, "last_smem")) { *value = msc::g_last_smem; return MSC_OK; }
     if (!strcmp(key, "last_fastdiv")) { *value = msc::g_last_fastdiv; return MSC_OK; }
-    if (!strcmp(key, "config")) { *value = msc::g_opt_config; return MSC_OK; }
     if (!strcmp(key, "tile_pts")) { *value = msc::g_last_tile_pts; return MSC_OK; }
     if (!strcmp(key, "stages")) { *value = msc::g_last_stages; return MSC_OK; }
     if (!strcmp(key, "threads")) { *value = msc::g_last_threads; return MSC_OK; }
@@ -695,18 +766,19 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
                              size_t workspace_bytes, void* stream_v) {
     using namespace msc;
     MSC_REQUIRE(params && in && out && workspace, "null argument");
-    MSC_REQUIRE(workspace_bytes >= 256, "workspace too small");
-    MSC_REQUIRE(in->n_samples >= 0, "negative n_samples");
+    MSC_REQUIRE(in->n_samples >= 0 && in->n_boxes >= 0, "negative counts");
     MSC_REQUIRE(params->n_cams >= 0 && params->n_cams <= MSC_MAX_CAMS, "n_cams out of range");
     MSC_REQUIRE(params->bev_res > 0 && params->bev_res <= 4096 && (params->bev_res & 1) == 0, "bev_res must be even and <= 4096");
-    MSC_REQUIRE(params->centroid_shift >= 0 && params->centroid_shift <= 20, "centroid_shift out of range");
+    MSC_REQUIRE(params->centroid_shift >= 0 && params->centroid_shift <= 17, "centroid_shift out of range (two 12-bit limbs hold 24 bits)");
     MSC_REQUIRE(params->intensity_shift >= 0 && params->intensity_shift <= 8, "intensity_shift out of range");
-    // the biased fixed-point coordinate must fit 27 bits: |c| * 2^shift < 2^(shift + 6)  <=>  |c| < 64 m
+    // the biased fixed-point coordinate must fit 24 bits: |c| * 2^shift < 2^(shift + 6)  <=>  |c| < 64 m
     MSC_REQUIRE(params->range_max < 64.0f && params->z_max < 64.0f && params->z_min > -64.0f, "range_max / z limits must be below 64 m");
-    const int32_t max_boxes_per_sample = in->max_boxes_per_sample;
-    MSC_REQUIRE(max_boxes_per_sample >= 0 && max_boxes_per_sample <= MSC_MAX_BOXES_FUSED, "more than %d boxes in one sample",
+    MSC_REQUIRE(in->max_boxes_per_sample >= 0 && in->max_boxes_per_sample <= MSC_MAX_BOXES_FUSED, "more than %d boxes in one sample",
                 MSC_MAX_BOXES_FUSED);
     MSC_REQUIRE((((uintptr_t)in->points) & 15) == 0, "points must be 16-byte aligned");
+    MSC_REQUIRE((((uintptr_t)workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    const TableLayout T = table_layout(*params, in->n_samples, in->n_boxes);
+    MSC_REQUIRE(workspace_bytes >= T.total, "workspace too small: need %zu bytes", T.total);
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (in->n_samples == 0) return MSC_OK;
     int dev = 0, sms = 0, smem_optin = 0;
@@ -717,7 +789,6 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     args.P = *params;
     args.in = *in;
     args.out = *out;
-    args.work_counter = reinterpret_cast<uint32_t*>(workspace);
     args.two_r = 2.0f * params->bev_range;
     args.resf = (float)params->bev_res;
     args.rcp_two_r = 1.0f / args.two_r;
@@ -728,12 +799,13 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     const bool fov = g_opt_fov != 0 && params->n_cams > 0;
     const bool fast = g_opt_fastdiv != 0 && fastdiv_verified(args.two_r);
     g_last_fastdiv = fast ? 1 : 0;
-    MSC_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    MSC_CUDA(cudaMemsetAsync(ws + T.counter_off, 0, 256, stream));
     const int grid = in->n_samples < sms ? in->n_samples : sms;
     switch (g_opt_config) {
-        case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
-        case 2: return dispatch_fused<Cfg<384, 2, 5>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
-        default: return dispatch_fused<Cfg<512, 2, 4>>(args, *params, max_boxes_per_sample, smem_optin, grid, fov, fast, stream);
+        case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        default: return dispatch_fused<Cfg<512, 2, 4>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
     }
 }
 

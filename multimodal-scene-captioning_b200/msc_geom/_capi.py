@@ -27,7 +27,8 @@ class MscParams(C.Structure):
 
 class MscBatchIn(C.Structure):
     _fields_ = [
-        ("n_samples", C.c_int32), ("max_boxes_per_sample", C.c_int32), ("points", C.c_void_p),
+        ("n_samples", C.c_int32), ("max_boxes_per_sample", C.c_int32), ("n_boxes", C.c_int32), ("reserved_", C.c_int32),
+        ("points", C.c_void_p),
         ("sample_sweep_off", C.c_void_p), ("sweep_start", C.c_void_p), ("sweep_count", C.c_void_p),
         ("sweep_pose", C.c_void_p), ("sample_box_off", C.c_void_p), ("boxes", C.c_void_p), ("ego_pose", C.c_void_p),
         ("lidar_calib", C.c_void_p), ("cam_ego_pose", C.c_void_p), ("cam_calib", C.c_void_p), ("cam_K", C.c_void_p),
@@ -47,7 +48,7 @@ _PROTOS = {
     "msc_abi_version": (C.c_int, []),
     "msc_last_error": (C.c_char_p, []),
     "msc_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 4),
-    "msc_fused_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "msc_fused_workspace_bytes": (C.c_size_t, [C.POINTER(MscParams), C.c_int32, C.c_int32]),
     "msc_fused_evidence_batch": (C.c_int, [C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
     "msc_fused_set_option": (C.c_int, [C.c_char_p, C.c_int32]),

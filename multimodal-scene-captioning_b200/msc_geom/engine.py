@@ -42,7 +42,7 @@ class DeviceBatch:
 
     def struct(self) -> MscBatchIn:
         t = self.tensors
-        return MscBatchIn(self.host.n_samples, self.host.max_boxes_per_sample, *[t[k].data_ptr() for k in _IN_FIELDS])
+        return MscBatchIn(self.host.n_samples, self.host.max_boxes_per_sample, self.host.n_boxes, 0, *[t[k].data_ptr() for k in _IN_FIELDS])
 
 
 @dataclass
@@ -138,12 +138,13 @@ class GeometryEngine:
             out = self.alloc_result(db.host, p)
         mp, bi, bo = make_params(p), db.struct(), out.struct()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        need = int(self.lib.msc_fused_workspace_bytes(C.byref(mp), db.host.n_samples, db.host.n_boxes))
         ws = self._workspaces.get(stream)
-        if ws is None:
-            ws = self._workspaces[stream] = torch.zeros(64, dtype=torch.int32, device=self.device)
-        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel() * 4,
+        if ws is None or ws.numel() < need:
+            ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
                                                       C.c_void_p(stream)), "msc_fused_evidence_batch")
-        self.kernel_launches += 1
+        self.kernel_launches += 2  # table kernel + streaming kernel
         return out
 
     def process_samples(self, samples: Sequence[dict], params: Optional[GeomParams] = None) -> Dict[str, np.ndarray]:

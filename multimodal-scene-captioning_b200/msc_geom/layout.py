@@ -37,7 +37,8 @@ class GeomParams:
     def centroid_shift(self) -> int:
         # 32 lanes x max |coordinate| x 2^shift must stay below 2^31 (REDUX-safe and s32-safe per point)
         m = max(abs(self.range_max), abs(self.z_min), abs(self.z_max), 1.0)
-        return int(min(20, np.floor(np.log2((2.0 ** 31) / 32.0 / m))))
+        # two 12-bit limbs per axis hold the biased coordinate: |c| < 64 m at 2^-17 m (7.6 um) resolution
+        return int(min(17, np.floor(np.log2((2.0 ** 23) / m))))
 
     def thresholds(self):
         return sqrt_thresholds(self.range_min, self.range_max)
