@@ -44,7 +44,8 @@ constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes 
 
 constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
 constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
-constexpr int kAccWords = 8;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs
+constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs; the odd
+                                              // stride spreads the same word of different boxes over all 32 banks
 constexpr int kMaxWarps = 32;
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
@@ -303,27 +304,28 @@ __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __re
     }
 }
 
-// A.2 exact membership test of one point against one prepared box + accumulator update.
-// Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis (each a fire-and-forget ATOMS).
-__device__ __forceinline__ void box_test_accumulate(const FusedArgs& A, const float* __restrict__ boxp, uint32_t* __restrict__ boxacc, int b,
-                                                    float xr, float yr, float zr, float s2) {
+// A.2 exact membership test of one point against one prepared box (closed intervals, float32 with fmaf chains).
+__device__ __forceinline__ bool box_contains(const float* __restrict__ boxp, int b, float xr, float yr, float zr) {
     const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
     const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
     const float v0 = __fsub_rn(xr, b0.x), v1 = __fsub_rn(yr, b0.y), v2 = __fsub_rn(zr, b0.z);
     const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
     const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
     const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
-    if (iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z && !(A.debug_skip & 8u)) {
-        uint32_t* acc = boxacc + b * kAccWords;
-        atomicAdd(acc + 0, 1u);
-        atomicMin(acc + 1, __float_as_uint(s2));
-        const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
-        const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
-        const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
-        atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
-        atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
-        atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
-    }
+    return iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z;
+}
+// Accumulator update of a member point.  Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis,
+// every update a fire-and-forget ATOMS (order-independent, bit-reproducible).
+__device__ __forceinline__ void box_accumulate(const FusedArgs& A, uint32_t* __restrict__ boxacc, int b, float xr, float yr, float zr, float s2) {
+    uint32_t* acc = boxacc + b * kAccWords;
+    atomicAdd(acc + 0, 1u);
+    atomicMin(acc + 1, __float_as_uint(s2));
+    const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
+    const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
+    const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
+    atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
+    atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
+    atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
 }
 
 template <class C, bool FOV, bool FASTDIV>
@@ -539,14 +541,24 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
                 // A.2 oriented-box membership for the candidate boxes of this cull cell
                 uint32_t ids = ce[u].x;
                 if (ids == kCullEmpty || (A.debug_skip & 2u)) continue;
+                // The divergent candidate loop only tests; the accumulator update of the (usually single) containing box runs
+                // once per point after the loop.  A second containing box (overlapping annotations) updates inside the loop.
+                int hit = -1;
                 if (ids == kCullAll) {  // crowded cell (more than four boxes): test every box
-                    for (int b = 0; b < n_boxes; ++b) box_test_accumulate(A, boxp, boxacc, b, xr[u], yr[u], zr[u], s2[u]);
-                    continue;
+                    for (int b = 0; b < n_boxes; ++b)
+                        if (box_contains(boxp, b, xr[u], yr[u], zr[u])) {
+                            if (hit >= 0) box_accumulate(A, boxacc, b, xr[u], yr[u], zr[u], s2[u]); else hit = b;
+                        }
+                } else {
+                    do {
+                        const int b = (int)(ids & 0xffu);
+                        if (box_contains(boxp, b, xr[u], yr[u], zr[u])) {
+                            if (hit >= 0) box_accumulate(A, boxacc, b, xr[u], yr[u], zr[u], s2[u]); else hit = b;
+                        }
+                        ids = (ids >> 8) | 0xff000000u;
+                    } while ((ids & 0xffu) != 0xffu);
                 }
-                do {
-                    box_test_accumulate(A, boxp, boxacc, (int)(ids & 0xffu), xr[u], yr[u], zr[u], s2[u]);
-                    ids = (ids >> 8) | 0xff000000u;
-                } while ((ids & 0xffu) != 0xffu);
+                if (hit >= 0 && !(A.debug_skip & 8u)) box_accumulate(A, boxacc, hit, xr[u], yr[u], zr[u], s2[u]);
             }
             ++wk;
             c_first += W * TP;
@@ -633,7 +645,7 @@ static int g_opt_window = 0;       // 0 = auto (largest that fits)
 static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
 static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
 static int g_opt_debug_skip = 0;
-static int g_opt_config = 0;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem
+static int g_opt_config = 2;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem
 static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 
 // divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
