@@ -202,7 +202,7 @@ def main():
     gathered = None
     if world > 1:
         tabs = out.table_tensors()
-        gathered = [torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in tabs]
+        gathered = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in tabs]
 
     def step():
         eng.run_fused(db, out)

@@ -396,14 +396,18 @@ void orc_annotation_table(int n, const double* xy, const double* vel, double* di
     static const double zmin[9] = {0, 10, 30, 0, 10, 0, 10, 0, 10};
     static const double zmax[9] = {10, 30, 50, 10, 30, 10, 30, 10, 30};
     static const uint8_t zdir[9] = {0, 0, 0, 1, 1, 3, 3, 2, 2};
+    /* The reference squares with Python's `**` (scenegraph_agent.py:189, :216), i.e. libm pow(), which is within 1 ulp
+     * of -- but not always equal to -- the correctly rounded product (1326.916**2 != 1326.916*1326.916).  The oracle
+     * follows the reference literally; `two` is volatile so the compiler cannot rewrite pow(x, 2.0) as x*x. */
+    volatile double two = 2.0;
     for (int i = 0; i < n; ++i) {
         double x = xy[2 * i], y = xy[2 * i + 1];
-        double d = sqrt(x * x + y * y);
+        double d = sqrt(pow(x, two) + pow(y, two));
         distance[i] = d;
         uint8_t dir = bearing4(x, y);
         direction[i] = dir;
         double vx = vel[2 * i], vy = vel[2 * i + 1];
-        double sp = sqrt(vx * vx + vy * vy);
+        double sp = sqrt(pow(vx, two) + pow(vy, two));
         moving[i] = (uint8_t)(sp > 0.5);
         uint8_t zc = 255;
         for (int k = 0; k < 9; ++k)

@@ -1,0 +1,58 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/msc_geom.h declares."""
+import ctypes
+import os
+import re
+
+from msc_geom import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "msc_geom.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = ctypes.CDLL(_capi.lib_path())
+    names = header_functions()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/msc_geom.h but not exported by libmsc_geom.so"
+
+
+def test_binding_covers_header_and_abi_version():
+    assert sorted(_capi.EXPORTED_SYMBOLS) == header_functions()
+    lib = _capi.load()
+    assert lib.msc_abi_version() == _capi.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes():
+    # msc_params: 16 x 4 bytes; msc_batch_in: 4 int32 + 12 pointers; msc_batch_out: 8 pointers
+    assert ctypes.sizeof(_capi.MscParams) == 64
+    assert ctypes.sizeof(_capi.MscBatchIn) == 16 + 12 * 8
+    assert ctypes.sizeof(_capi.MscBatchOut) == 8 * 8
+
+
+def test_no_cpu_fallback():
+    """Without a device the product path must fail loudly, not fall back."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from msc_geom.engine import GeometryEngine
+    with pytest.raises(_capi.MscError):
+        GeometryEngine()
+    s = ctypes.c_int32()
+    rc = _capi.load().msc_device_info(ctypes.byref(s), None, None, None)
+    assert rc != 0 and b"device" in _capi.load().msc_last_error().lower()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodal-scene-captioning_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f in ("synthetic.py",), f"{f} mentions the oracle"

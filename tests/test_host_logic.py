@@ -1,0 +1,84 @@
+"""Host-side logic: batch layout, pose algebra, exact thresholds, sharding."""
+import numpy as np
+import pytest
+
+from msc_geom import geometry as G
+from msc_geom.dist import shard_range
+from msc_geom.layout import GeomParams, pack_batch, tile_batch
+from msc_geom.synthetic import make_sample
+
+
+def test_sqrt_thresholds_are_exact():
+    s_lo, s_hi = G.sqrt_thresholds(1.0, 50.0)
+    for thr, base in ((np.float32(1.0), np.float32(s_lo)), (np.float32(50.0), np.float32(s_hi))):
+        s = base
+        for _ in range(2000):
+            s = np.nextafter(s, np.float32(-np.inf))
+        for _ in range(4000):
+            d = np.sqrt(s)
+            if thr == 1.0:
+                assert (d > thr) == (s >= np.float32(s_lo))
+            else:
+                assert (d < thr) == (s <= np.float32(s_hi))
+            s = np.nextafter(s, np.float32(np.inf))
+    rng = np.random.default_rng(0)
+    s = rng.uniform(0, 3000, 200000).astype(np.float32)
+    d = np.sqrt(s)
+    assert np.array_equal((d > 1.0) & (d < 50.0), (s >= np.float32(s_lo)) & (s <= np.float32(s_hi)))
+
+
+def test_ref_from_sweep_identity_and_inverse():
+    s = make_sample(3, n_sweeps=4)
+    M0 = s["lidar_sweeps"][0]["ref_from_sensor"]
+    assert np.allclose(M0, np.eye(4)[:3], atol=1e-12)
+    sw = s["lidar_sweeps"][2]
+    M = np.vstack([sw["ref_from_sensor"], [0, 0, 0, 1]])
+    back = np.vstack([G.ref_from_sweep(sw["ego_pose"], sw["calib"], s["ego_pose"], s["lidar_calib"]), [0, 0, 0, 1]])
+    assert np.allclose(M @ back, np.eye(4), atol=1e-9)
+    R = G.quat_to_rot(G.rot_to_quat(M[:3, :3]))
+    assert np.allclose(R, M[:3, :3], atol=1e-12)
+
+
+def test_pack_batch_layout():
+    samples = [make_sample(i, n_sweeps=3 if i else 2, n_boxes=5 + i) for i in range(3)]
+    samples[1]["lidar_sweeps"][1]["points_raw"] = samples[1]["lidar_sweeps"][1]["points_raw"][:1001]  # ragged sweep
+    hb = pack_batch(samples)
+    assert hb.n_samples == 3 and hb.sample_sweep_off.tolist() == [0, 2, 5, 8]
+    assert (hb.sweep_start % 4 == 0).all(), "16-byte aligned sweep starts"
+    assert hb.points.shape[0] >= int(hb.sweep_start[-1] + hb.sweep_count[-1]) + 4
+    k = 0
+    for s in samples:
+        for sw in s["lidar_sweeps"]:
+            a, n = int(hb.sweep_start[k]), int(hb.sweep_count[k])
+            assert np.array_equal(hb.points[a:a + n], sw["points_raw"])
+            assert np.array_equal(hb.sweep_pose[k].reshape(3, 4), sw["ref_from_sensor"])
+            k += 1
+    pad = hb.points[int(hb.sweep_start[3] + hb.sweep_count[3]): int(hb.sweep_start[4])]
+    assert pad.shape[0] == 3 and np.isnan(pad).all(), "padding rows are NaN so they fail every compare"
+    assert hb.sample_box_off.tolist() == [0, 5, 11, 18] and hb.max_boxes_per_sample == 7
+    assert np.array_equal(hb.boxes[5, :3], samples[1]["annotations"][0]["translation"])
+    t = tile_batch(hb, 3)
+    assert t.n_samples == 9 and t.n_points == 3 * hb.n_points and t.boxes.shape[0] == 3 * hb.boxes.shape[0]
+    a, n = int(t.sweep_start[8 + 2]), int(t.sweep_count[8 + 2])
+    assert np.array_equal(t.points[a:a + n], samples[1]["lidar_sweeps"][0]["points_raw"])
+
+
+def test_plain_loader_sample_becomes_identity_sweep():
+    pc = np.random.default_rng(1).normal(size=(100, 4)).astype(np.float32)
+    hb = pack_batch([{"point_cloud": pc, "annotations": []}])
+    assert hb.sweep_count.tolist() == [100] and np.array_equal(hb.points[:100, :4], pc)
+    assert np.array_equal(hb.sweep_pose[0].reshape(3, 4), np.eye(4)[:3])
+
+
+def test_params_defaults_follow_reference():
+    p = GeomParams()
+    assert (p.range_min, p.range_max, p.z_min, p.z_max, p.ground_z, p.bev_range) == (1.0, 50.0, -3.0, 5.0, -1.4, 50.0)
+    assert p.centroid_shift == 17 and GeomParams(range_max=20.0).centroid_shift == 17 and p.intensity_shift == 8
+
+
+@pytest.mark.parametrize("n,world", [(404, 8), (34149, 8), (5, 8), (0, 2), (592, 1)])
+def test_shard_range_partitions(n, world):
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert max(hi - lo for lo, hi in spans) == (n + world - 1) // world if n else True
