@@ -1,0 +1,199 @@
+"""Thin host wrappers over the single-sample / small-table entry points of the C-ABI (include/msc_geom.h).
+Inputs and outputs are NumPy arrays on the host (the reference's functions take and return NumPy); device buffers
+are torch tensors that live for the duration of the call."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from .engine import GeometryEngine, make_params
+from .layout import GeomParams
+
+
+def _stream(eng: GeometryEngine):
+    return C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+
+
+def _raw_rows(pc: np.ndarray) -> Tuple[np.ndarray, int]:
+    """Return a C-contiguous float32 buffer and its row pitch (floats) for an (N, >=4) cloud WITHOUT repacking the
+    devkit's 20-byte-pitch view (nuscenes_loader.py:152-155: (N,5)[:, :4] seen through two transposes)."""
+    pc = np.asarray(pc)
+    if pc.dtype != np.float32:
+        pc = pc.astype(np.float32)
+    n = pc.shape[0]
+    if n == 0:
+        return np.zeros((0, 4), np.float32), 4
+    if pc.flags["C_CONTIGUOUS"]:
+        return pc, pc.shape[1]
+    if pc.ndim == 2 and pc.strides[1] == 4 and pc.strides[0] % 4 == 0 and pc.strides[0] // 4 >= pc.shape[1]:
+        pitch = pc.strides[0] // 4
+        base = pc
+        while isinstance(base.base, np.ndarray):
+            base = base.base
+        lo = base.__array_interface__["data"][0]
+        hi = lo + base.nbytes
+        start = pc.__array_interface__["data"][0]
+        if lo <= start and start + n * pitch * 4 <= hi:
+            return np.lib.stride_tricks.as_strided(pc, shape=(n, pitch), strides=(pitch * 4, 4)), pitch
+    return np.ascontiguousarray(pc), pc.shape[1]
+
+
+def keyframe_filter_split(eng: GeometryEngine, pc: np.ndarray, params: Optional[GeomParams] = None):
+    """LiDARAgent._preprocess_point_cloud + _segment_ground (lidar_agent.py:103-132): kept, ground, object as (n,4) f32."""
+    p = params or GeomParams(bev_res=800)
+    rows, pitch = _raw_rows(pc)
+    n = rows.shape[0]
+    d = eng.device
+    if n == 0:
+        z = np.zeros((0, 4), np.float32)
+        return z, z.copy(), z.copy()
+    src = torch.from_numpy(np.ascontiguousarray(rows)).to(d)
+    kept = torch.empty((n, 4), dtype=torch.float32, device=d)
+    ground = torch.empty((n, 4), dtype=torch.float32, device=d)
+    obj = torch.empty((n, 4), dtype=torch.float32, device=d)
+    counts = torch.zeros(3, dtype=torch.int32, device=d)
+    n_blocks = (n + 1023) // 1024
+    scratch = torch.empty(n_blocks * 2 + 2, dtype=torch.int32, device=d)
+    mp = make_params(p)
+    _capi.check(eng.lib.msc_keyframe_filter_split(C.byref(mp), src.data_ptr(), n, pitch, kept.data_ptr(), ground.data_ptr(), obj.data_ptr(),
+                                                  counts.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(eng)), "msc_keyframe_filter_split")
+    eng.kernel_launches += 3
+    nk, ng, no = (int(v) for v in counts.cpu().tolist())
+    return kept[:nk].cpu().numpy(), ground[:ng].cpu().numpy(), obj[:no].cpu().numpy()
+
+
+def keyframe_bev_layers(eng: GeometryEngine, ground: np.ndarray, obj: np.ndarray, res: int = 800, bev_range: float = 50.0):
+    """Raster half of _generate_multi_layer_bev (lidar_agent.py:539-597): count u32, height f32, semantic BGR u8 (unflipped)."""
+    p = GeomParams(bev_res=res, bev_range=bev_range)
+    d = eng.device
+    g = torch.from_numpy(np.ascontiguousarray(ground[:, :4], np.float32)).to(d) if len(ground) else torch.zeros((1, 4), device=d)
+    o = torch.from_numpy(np.ascontiguousarray(obj[:, :4], np.float32)).to(d) if len(obj) else torch.zeros((1, 4), device=d)
+    count = torch.empty((res, res), dtype=torch.int32, device=d)
+    height = torch.empty((res, res), dtype=torch.float32, device=d)
+    sem = torch.empty((res, res, 3), dtype=torch.uint8, device=d)
+    winner = torch.empty((res, res), dtype=torch.int32, device=d)
+    zr = torch.empty(2, dtype=torch.int32, device=d)
+    mp = make_params(p)
+    _capi.check(eng.lib.msc_keyframe_bev(C.byref(mp), g.data_ptr(), len(ground), o.data_ptr(), len(obj), count.data_ptr(), height.data_ptr(),
+                                         sem.data_ptr(), winner.data_ptr(), zr.data_ptr(), _stream(eng)), "msc_keyframe_bev")
+    eng.kernel_launches += 2
+    return count.cpu().numpy().view(np.uint32), height.cpu().numpy(), sem.cpu().numpy()
+
+
+def cloud_stats(eng: GeometryEngine, pc: np.ndarray):
+    """RawGPT4oBaseline._describe_point_cloud numbers (baseline_gpt4o.py:276-285): (min3, max3, mean radial distance)."""
+    rows, pitch = _raw_rows(pc)
+    n = rows.shape[0]
+    if n == 0:
+        return None
+    src = torch.from_numpy(np.ascontiguousarray(rows)).to(eng.device)
+    out = torch.zeros(7, dtype=torch.float64, device=eng.device)
+    _capi.check(eng.lib.msc_cloud_stats(src.data_ptr(), n, pitch, out.data_ptr(), _stream(eng)), "msc_cloud_stats")
+    eng.kernel_launches += 2
+    o = out.cpu().numpy()
+    return o[:3].astype(np.float32), o[3:6].astype(np.float32), float(o[6] / n)
+
+
+def cluster_aabb(eng: GeometryEngine, pts: np.ndarray, labels: np.ndarray, n_clusters: int) -> np.ndarray:
+    """Per-cluster min3, max3, center3, distance, num_points (lidar_agent.py:200-204) for DBSCAN labels."""
+    if n_clusters == 0:
+        return np.zeros((0, 11), np.float32)
+    rows, pitch = _raw_rows(pts)
+    src = torch.from_numpy(np.ascontiguousarray(rows)).to(eng.device)
+    lab = torch.from_numpy(np.ascontiguousarray(labels, np.int32)).to(eng.device)
+    out = torch.empty((n_clusters, 11), dtype=torch.float32, device=eng.device)
+    _capi.check(eng.lib.msc_cluster_aabb(src.data_ptr(), rows.shape[0], pitch, lab.data_ptr(), n_clusters, out.data_ptr(), _stream(eng)),
+                "msc_cluster_aabb")
+    eng.kernel_launches += 3
+    return out.cpu().numpy()
+
+
+def annotation_table(eng: GeometryEngine, xy: np.ndarray, vel: np.ndarray) -> Dict[str, np.ndarray]:
+    """Numeric half of SceneGraphAgent._parse_annotations / _build_spatial_zones (scenegraph_agent.py:186-225, :281-295)."""
+    n = int(xy.shape[0])
+    d = eng.device
+    if n == 0:
+        return {"distance": np.zeros(0), "direction": np.zeros(0, np.uint8), "moving": np.zeros(0, np.uint8), "zone": np.zeros(0, np.uint8),
+                "region_bits": np.zeros(0, np.uint8)}
+    x = torch.from_numpy(np.ascontiguousarray(xy, np.float64)).to(d)
+    v = torch.from_numpy(np.ascontiguousarray(vel, np.float64)).to(d)
+    dist = torch.empty(n, dtype=torch.float64, device=d)
+    u8 = [torch.empty(n, dtype=torch.uint8, device=d) for _ in range(4)]
+    _capi.check(eng.lib.msc_annotation_table(n, x.data_ptr(), v.data_ptr(), dist.data_ptr(), *[t.data_ptr() for t in u8], _stream(eng)),
+                "msc_annotation_table")
+    eng.kernel_launches += 1
+    return {"distance": dist.cpu().numpy(), "direction": u8[0].cpu().numpy(), "moving": u8[1].cpu().numpy(), "zone": u8[2].cpu().numpy(),
+            "region_bits": u8[3].cpu().numpy()}
+
+
+def relation_table(eng: GeometryEngine, boxes: np.ndarray, ego_pose: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """[EXT] pairwise relations (distance, bearing, 4-way category, footprint overlap) between n annotation boxes."""
+    n = int(boxes.shape[0])
+    d = eng.device
+    if n == 0:
+        z = np.zeros((0, 0))
+        return {"dist": z.astype(np.float32), "bearing": z.astype(np.float32), "category": z.astype(np.uint8), "overlap": z.astype(np.uint8), "rect": np.zeros((0, 6))}
+    b = torch.from_numpy(np.ascontiguousarray(boxes, np.float64)).to(d)
+    rect = torch.empty((n, 6), dtype=torch.float64, device=d)
+    ego = None if ego_pose is None else torch.from_numpy(np.ascontiguousarray(ego_pose, np.float64)).to(d)
+    _capi.check(eng.lib.msc_box_footprints(n, b.data_ptr(), ego.data_ptr() if ego is not None else None, rect.data_ptr(), _stream(eng)), "msc_box_footprints")
+    dist = torch.empty((n, n), dtype=torch.float32, device=d)
+    bearing = torch.empty((n, n), dtype=torch.float32, device=d)
+    cat = torch.empty((n, n), dtype=torch.uint8, device=d)
+    ov = torch.empty((n, n), dtype=torch.uint8, device=d)
+    _capi.check(eng.lib.msc_relation_table(n, rect.data_ptr(), dist.data_ptr(), bearing.data_ptr(), cat.data_ptr(), ov.data_ptr(), _stream(eng)),
+                "msc_relation_table")
+    eng.kernel_launches += 2
+    return {"dist": dist.cpu().numpy(), "bearing": bearing.cpu().numpy(), "category": cat.cpu().numpy(), "overlap": ov.cpu().numpy(),
+            "rect": rect.cpu().numpy()}
+
+
+def project_boxes(eng: GeometryEngine, boxes: np.ndarray, cam_ego_pose: np.ndarray, cam_calib: np.ndarray, cam_K: np.ndarray, image_w=1600, image_h=900):
+    """[EXT] box -> camera projection for one sample: visible [B,C] u8, extent [B,C,4] f32."""
+    nb, nc = int(boxes.shape[0]), int(cam_calib.shape[0])
+    d = eng.device
+    if nb == 0 or nc == 0:
+        return np.zeros((nb, nc), np.uint8), np.zeros((nb, nc, 4), np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(d)
+    b, p, c, k = t(boxes), t(cam_ego_pose), t(cam_calib), t(np.asarray(cam_K).reshape(nc, 9))
+    vis = torch.empty((nb, nc), dtype=torch.uint8, device=d)
+    ext = torch.empty((nb, nc, 4), dtype=torch.float32, device=d)
+    _capi.check(eng.lib.msc_project_boxes(nb, b.data_ptr(), nc, p.data_ptr(), c.data_ptr(), k.data_ptr(), image_w, image_h, vis.data_ptr(),
+                                          ext.data_ptr(), _stream(eng)), "msc_project_boxes")
+    eng.kernel_launches += 1
+    return vis.cpu().numpy(), ext.cpu().numpy()
+
+
+def aggregate_sweeps(eng: GeometryEngine, sweeps, remove_close_radius: float = 1.0):
+    """[EXT] devkit LidarPointCloud.from_file_multisweep (App. A.1): sweeps = [(raw (n,5) f32, M 3x4 f64, time_lag)];
+    returns (N,4) f32 rows x', y', z', intensity and (N,) f32 time lags, order-preserving."""
+    if not sweeps:
+        return np.zeros((0, 4), np.float32), np.zeros(0, np.float32)
+    d = eng.device
+    counts = np.array([s[0].shape[0] for s in sweeps], np.uint32)
+    starts = np.zeros(len(sweeps), np.uint32)
+    starts[1:] = np.cumsum(counts)[:-1]
+    total = int(counts.sum())
+    if total == 0:
+        return np.zeros((0, 4), np.float32), np.zeros(0, np.float32)
+    pts = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.asarray(s[0], np.float32) for s in sweeps], 0))).to(d)
+    pose = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(s[1], np.float64).reshape(-1)[:12] for s in sweeps]))).to(d)
+    lag = torch.from_numpy(np.array([s[2] for s in sweeps], np.float32)).to(d)
+    st = torch.from_numpy(starts.view(np.int32)).to(d)
+    ct = torch.from_numpy(counts.view(np.int32)).to(d)
+    max_pts = int(counts.max())
+    n_blocks = (len(sweeps) * max_pts + 1023) // 1024
+    scratch = torch.empty(n_blocks * 2 + 8, dtype=torch.int32, device=d)
+    out = torch.empty((total, 4), dtype=torch.float32, device=d)
+    out_t = torch.empty(total, dtype=torch.float32, device=d)
+    n_out = torch.zeros(1, dtype=torch.int32, device=d)
+    _capi.check(eng.lib.msc_aggregate_sweeps(C.c_float(remove_close_radius), pts.data_ptr(), len(sweeps), st.data_ptr(), ct.data_ptr(), pose.data_ptr(),
+                                             lag.data_ptr(), max_pts, out.data_ptr(), out_t.data_ptr(), n_out.data_ptr(), scratch.data_ptr(),
+                                             scratch.numel(), _stream(eng)), "msc_aggregate_sweeps")
+    eng.kernel_launches += 3
+    m = int(n_out.item())
+    return out[:m].cpu().numpy(), out_t[:m].cpu().numpy()

@@ -1,0 +1,326 @@
+"""GPU parity tests: every CUDA entry point of the C-ABI against the oracle and the reference-generated goldens.
+Bar: bit-exact for integer / byte / index outputs and for order-independent floats; float tolerances are written
+where an order- or library-dependent float is compared."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from msc_geom import _capi, ops
+from msc_geom.layout import GeomParams, HostBatch, boxes_from_annotations, pack_batch, tile_batch
+from msc_geom.synthetic import edge_case_cloud, make_sample
+from tests import oracle_bridge as OB
+
+IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
+
+
+def check_fused(eng, samples, params=None, config=2, n_cams=6):
+    p = params or GeomParams()
+    _capi.set_option("config", config)
+    hb = pack_batch(samples, n_cams=n_cams)
+    out = eng.run_fused(eng.upload(hb), params=p)
+    import torch
+    torch.cuda.synchronize()
+    got = out.to_host()
+    for i in range(hb.n_samples):
+        ref = OB.oracle_fused(hb, i, p)
+        b0, b1 = hb.sample_box_off[i], hb.sample_box_off[i + 1]
+        for k in ("box_count", "box_nearest", "box_centroid", "proj_visible", "proj_extent"):
+            assert np.array_equal(got[k][b0:b1], ref[k], equal_nan=True), (i, k)
+        for k in ("bev_count", "bev_isum_q", "bev_height"):
+            assert np.array_equal(got[k][i], ref[k]), (i, k, int((got[k][i] != ref[k]).sum()))
+        assert np.array_equal(got["stats"][i][:13], ref["stats"][:13]), (i, got["stats"][i], ref["stats"])
+        # size-independent invariants
+        st = got["stats"][i]
+        assert st[3] + st[4] == st[2] and int(got["bev_count"][i].sum()) == st[2] and st[1] <= st[0]
+    return hb, got
+
+
+@pytest.mark.parametrize("config", [0, 1, 2])
+def test_fused_config3_shape(engine, config):
+    check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
+
+
+def test_fused_mini_boxes_and_mixed_sweeps(engine):
+    check_fused(engine, [make_sample(20 + i, n_sweeps=1 + 3 * (i % 3), n_boxes="mini") for i in range(4)])
+
+
+def test_fused_ragged_and_empty_inputs(engine):
+    a = make_sample(30, n_sweeps=4, n_boxes=7)
+    sw = a["lidar_sweeps"]
+    sw[0]["points_raw"] = sw[0]["points_raw"][:1001]          # not a multiple of 4 or 64
+    sw[1]["points_raw"] = sw[1]["points_raw"][:0]             # empty sweep
+    sw[2]["points_raw"] = sw[2]["points_raw"][:63]            # shorter than one warp tile
+    sw[3]["points_raw"] = sw[3]["points_raw"][:64 * 32 + 1]   # one point into the next round of warp tiles
+    b = make_sample(31, n_sweeps=2, n_boxes=0)                # no boxes
+    c = make_sample(32, n_sweeps=1, n_boxes=3)
+    c["lidar_sweeps"] = [dict(c["lidar_sweeps"][0], points_raw=c["lidar_sweeps"][0]["points_raw"][:0])]  # no points at all
+    d = {"point_cloud": np.random.default_rng(5).normal(0, 12, (5000, 4)).astype(np.float32), "annotations": []}  # plain reference-style sample
+    for cfg in (1, 2):
+        check_fused(engine, [a, b, c, d], config=cfg)
+
+
+def test_fused_crowded_cell_and_max_boxes(engine):
+    s = make_sample(40, n_sweeps=2, n_boxes=60)
+    base = s["annotations"][0]
+    for k in range(9):  # nine boxes stacked on one spot: more than four ids per cull cell -> test-every-box path
+        a = dict(s["annotations"][1 + k])
+        a["translation"] = [base["translation"][0] + 0.05 * k, base["translation"][1], base["translation"][2]]
+        a["rotation"] = base["rotation"]
+        a["size"] = base["size"]
+        s["annotations"][1 + k] = a
+    hb, got = check_fused(engine, [s])
+    assert got["box_count"][:10].min() > 0
+    big = make_sample(41, n_sweeps=1, n_boxes=255)
+    check_fused(engine, [big])
+
+
+def test_fused_fov_filter_and_weird_values(engine):
+    s = make_sample(50, n_sweeps=3, n_boxes=30)
+    raw = s["lidar_sweeps"][1]["points_raw"]
+    raw[::7, 3] = -5.0          # negative intensity clamps to 0
+    raw[1::7, 3] = 300.25       # clamps to 65535 / 256
+    raw[2::7, 3] = np.nan
+    raw[3::11, 0] = np.nan      # NaN coordinates fail every compare
+    raw[5::13, 2] = np.inf
+    raw[6::17, 3] = 17.123
+    check_fused(engine, [s])
+    check_fused(engine, [s], params=GeomParams(fov_keep_mask=0b000001))
+    check_fused(engine, [s], params=GeomParams(fov_keep_mask=0b101000))
+
+
+def test_fused_threshold_points_identity_pose(engine):
+    """Points exactly on every strict threshold (lidar_agent.py:106-110, :128) and BEV cell edge, through an identity sweep."""
+    pc = edge_case_cloud()
+    rng = np.random.default_rng(3)
+    extra = np.stack([np.float32(v) for v in (49.999996, -49.999996, 1.0000001, 7.4999995)]).astype(np.float32)
+    pts = np.concatenate([pc, np.stack([rng.choice(extra, 500), rng.choice(extra, 500), rng.uniform(-3, 5, 500).astype(np.float32),
+                                        rng.uniform(0, 255, 500).astype(np.float32)], 1)])
+    anns = []
+    for cx, cy in [(10.0, 0.0), (-7.0, 3.0), (3.0, -7.0)]:  # axis-aligned boxes whose faces pass through many of the grid-aligned points
+        anns.append({"category_name": "vehicle.car", "translation": [cx, cy, 0.0], "size": [2.0, 4.0, 2.0], "rotation": [1.0, 0.0, 0.0, 0.0]})
+    sample = {"point_cloud": pts, "annotations": anns, "ego_pose": IDENT7, "lidar_calib": IDENT7}
+    hb, got = check_fused(engine, [sample], n_cams=6)
+    assert got["box_count"].sum() > 0
+
+
+def test_fused_other_grid_and_exact_division_path(engine):
+    """A divisor that is not on the Markstein whitelist takes the IEEE-division instantiation."""
+    s = [make_sample(60 + i, n_sweeps=2, n_boxes=25) for i in range(2)]
+    check_fused(engine, s, params=GeomParams(range_max=40.0, bev_range=45.0, bev_res=150))
+    assert _capi.get_option("last_fastdiv") == 0
+    check_fused(engine, s, params=GeomParams(range_max=30.0, bev_range=32.0, bev_res=128, z_max=3.0, ground_z=-1.0, remove_close_radius=2.5))
+    check_fused(engine, s)
+    assert _capi.get_option("last_fastdiv") == 1
+
+
+def test_fused_fov_counts_off_and_small_window(engine):
+    s = [make_sample(70, n_sweeps=2, n_boxes=20)]
+    _capi.set_option("fov", 0)
+    try:
+        p = GeomParams()
+        hb = pack_batch(s)
+        import torch
+        got = engine.run_fused(engine.upload(hb), params=p); torch.cuda.synchronize(); got = got.to_host()
+        ref = OB.oracle_fused(hb, 0, p)
+        assert np.array_equal(got["stats"][0][:5], ref["stats"][:5]) and (got["stats"][0][5:13] == 0).all()
+        assert np.array_equal(got["bev_count"][0], ref["bev_count"]) and np.array_equal(got["box_count"], ref["box_count"])
+    finally:
+        _capi.set_option("fov", 1)
+    for w in (2, 40, 0):  # almost everything through the 64-bit global reductions, then the default window
+        _capi.set_option("window", w)
+        check_fused(engine, s)
+    _capi.set_option("window", 0)
+
+
+def test_fused_full_size_batch_properties(engine):
+    """BASELINE config-3 batch at the benchmark's size (592 samples, 205.5 M points): size-independent properties, replica
+    equality (bit-reproducibility under different scheduling), idempotence, and the oracle on sampled samples."""
+    import torch
+    p = GeomParams()
+    _capi.set_option("config", 2)
+    uniq = [make_sample(100 + i, n_sweeps=10, n_boxes=60) for i in range(8)]
+    hb_u = pack_batch(uniq)
+    hb = tile_batch(hb_u, 74)
+    assert hb.n_samples == 592
+    db = engine.upload(hb)
+    out = engine.run_fused(db, params=p); torch.cuda.synchronize()
+    got = out.to_host(with_bev=False)
+    cnt = out.bev_ci[..., 0]
+    st = got["stats"]
+    assert (st[:, 0] == 347200).all() and (st[:, 3] + st[:, 4] == st[:, 2]).all()
+    assert torch.equal(cnt.sum(dim=(1, 2)).cpu(), torch.from_numpy(st[:, 2].astype(np.int64)).to(torch.int64))
+    nb = hb_u.n_boxes
+    for k in ("box_count", "box_nearest", "box_centroid", "proj_visible", "proj_extent"):
+        a = got[k].reshape((74, nb) + got[k].shape[1:])
+        assert (a == a[0:1]).all(), k                       # every replica bit-identical
+    assert (st.reshape(74, 8, 16) == st.reshape(74, 8, 16)[0:1]).all()
+    assert torch.equal(out.bev_ci[:8], out.bev_ci[8 * 73: 8 * 74]) and torch.equal(out.bev_height[:8], out.bev_height[8 * 37: 8 * 38])
+    out2 = engine.run_fused(db, params=p); torch.cuda.synchronize()   # idempotent: outputs are fully rewritten
+    assert torch.equal(out.bev_ci, out2.bev_ci) and torch.equal(out.box_centroid, out2.box_centroid)
+    for i in (3, 6):
+        ref = OB.oracle_fused(hb_u, i, p)
+        b0, b1 = hb_u.sample_box_off[i], hb_u.sample_box_off[i + 1]
+        assert np.array_equal(got["box_count"][b0:b1], ref["box_count"]) and np.array_equal(got["box_centroid"][b0:b1], ref["box_centroid"])
+        assert np.array_equal(out.bev_ci[i, ..., 0].cpu().numpy().view(np.uint32), ref["bev_count"])
+        assert np.array_equal(out.bev_height[i].cpu().numpy(), ref["bev_height"])
+
+
+# ------------------------------------------------------------------------------------------------ keyframe path vs the reference
+@pytest.mark.parametrize("name", ["mock", "edge", "synth", "empty", "flatobj"])
+def test_keyframe_filter_split_and_bev_match_reference(engine, golden_dir, name):
+    from msc_geom.lidar_agent import LiDARAgent
+    g = np.load(os.path.join(golden_dir, f"keyframe_{name}.npz"))
+    agent = LiDARAgent(object(), "m", "n", engine=engine)
+    kept = agent._preprocess_point_cloud(g["points"])
+    ground, obj = agent._segment_ground(kept)
+    assert np.array_equal(kept, g["kept"]) and np.array_equal(ground, g["ground"]) and np.array_equal(obj, g["object"])
+    bev = agent._generate_multi_layer_bev(ground, obj)
+    for k in ("semantic", "height", "density"):
+        assert bev[k].dtype == g[k].dtype and np.array_equal(bev[k], g[k]), (name, k)
+
+
+def test_keyframe_strided_devkit_view(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "keyframe_synth.npz"))
+    raw = np.zeros((g["points"].shape[0], 5), np.float32)
+    raw[:, :4] = g["points"]; raw[:, 4] = 7.0
+    view = raw[:, :4]                                  # 20-byte pitch, like nuscenes_loader.py:152-155
+    rows, pitch = ops._raw_rows(view)
+    assert pitch == 5 and rows.__array_interface__["data"][0] == raw.__array_interface__["data"][0]  # no host repack
+    kept, ground, obj = ops.keyframe_filter_split(engine, view, GeomParams(bev_res=800))
+    assert np.array_equal(kept, g["kept"]) and np.array_equal(obj, g["object"])
+
+
+def test_lidar_agent_process_matches_reference(engine, golden_dir, golden_json):
+    from msc_geom.lidar_agent import LiDARAgent
+    from msc_geom.nuscenes_loader import create_loader
+    np.random.seed(0)
+    sample = create_loader(None, use_mock=True).get_sample_by_scene_index(0, 0)
+    agent = LiDARAgent(object(), "m", "LiDARAgent", engine=engine, llm=lambda *a, **k: "STUB",
+                       cluster_classifier=lambda batch: [{"category": "car", "confidence": 0.9} for _ in batch])
+    out = agent.process(sample["point_cloud"])
+    ref = golden_json["process_mock"]
+    assert out["bev_metadata"] == ref["bev_metadata"] and out["structured_report"] == ref["structured_report"]
+    assert out["observations"] == ref["observations"] and out["agent"] == "LiDARAgent" and out["modality"] == "lidar"
+    sf = dict(out["semantic_features"]); near = sf.pop("nearest_object")
+    rf = dict(ref["semantic_features"]); rd = rf.pop("nearest_object_distance")
+    assert sf == rf and ((near is None and rd is None) or float(near.distance) == rd)
+    assert json.loads(json.dumps(out["detected_objects"])) == ref["detected_objects"]
+
+
+def test_cluster_metadata_matches_reference(engine, golden_dir):
+    from msc_geom.lidar_agent import LiDARAgent
+    g = np.load(os.path.join(golden_dir, "clusters_synth.npz"))
+    agent = LiDARAgent(object(), "m", "n", engine=engine)
+    labels = g["labels"]
+    order = [int(l) for l in set(labels.tolist()) if l != -1 and (labels == l).sum() >= 5]
+    meta = agent._cluster_metadata(g["object"], labels, order)
+    assert len(meta) == len(g["num_points"])
+    for i, m in enumerate(meta):
+        assert np.array_equal(m["center"], g["center"][i]) and np.array_equal(m["dimensions"], g["dimensions"][i])
+        assert m["distance"] == g["distance"][i] and m["num_points"] == g["num_points"][i] and m["direction"] == str(g["direction"][i])
+
+
+@pytest.mark.parametrize("case", ["mock", "docs_scene_1", "docs_scene_2", "docs_scene_3", "edge"])
+def test_scenegraph_agent_matches_reference(engine, golden_json, case):
+    from msc_geom.scenegraph_agent import SceneGraphAgent
+    g = golden_json["annotations"][case]
+    agent = SceneGraphAgent(object(), "m", "SceneGraphAgent", engine=engine)
+    objs = agent._parse_annotations(g["annotations"])
+    assert len(objs) == len(g["parsed"])
+    for a, b in zip(objs, g["parsed"]):
+        for k in ("id", "category", "direction", "state", "visibility", "attributes", "position"):
+            assert a[k] == b[k], (k, a, b)
+        # the reference squares with libm pow (1 ulp from the exact product for some inputs): 1e-5 relative is the bar, 2 ulp is what we hold
+        assert abs(float(a["distance"]) - b["distance"]) <= 2 * np.spacing(b["distance"]) or (np.isnan(a["distance"]) and np.isnan(b["distance"]))
+    assert {k: [o["id"] for o in v] for k, v in agent._categorize_objects(objs).items()} == g["categorized"]
+    assert {k: [o["id"] for o in v] for k, v in agent._build_spatial_zones(objs).items()} == g["zones"]
+    if g["describe"] is not None:
+        rc = agent.region_counts(g["annotations"])
+        for name in ("front", "back", "left", "right"):
+            assert f"- {name.capitalize()} region: {rc[name]} objects" in g["describe"]
+
+
+def test_cloud_stats_match_reference(engine, golden_dir, golden_json):
+    pts = np.load(os.path.join(golden_dir, "keyframe_mock.npz"))["points"]
+    mn, mx, mean = ops.cloud_stats(engine, pts)
+    assert np.array_equal(mn, pts[:, :3].min(0)) and np.array_equal(mx, pts[:, :3].max(0))
+    text = golden_json["describe_point_cloud_mock"]
+    assert f"X range: [{mn[0]:.1f}, {mx[0]:.1f}] m" in text and f"Z range: [{mn[2]:.1f}, {mx[2]:.1f}] m" in text
+    assert f"Average distance from ego: {mean:.1f} m" in text
+    assert abs(mean - OB.oracle_cloud_stats(pts)[1] / len(pts)) <= 1e-12 * mean  # f64 accumulation, order differs
+
+
+# ------------------------------------------------------------------------------------------------ [EXT] tables vs the oracle
+def test_aggregate_sweeps_bit_exact(engine):
+    s = make_sample(80, n_sweeps=5)
+    s["lidar_sweeps"][2]["points_raw"] = s["lidar_sweeps"][2]["points_raw"][:777]
+    hb = pack_batch([s])
+    ref_xyzi, ref_t = OB.oracle_aggregate(hb, 0)
+    xyzi, t = ops.aggregate_sweeps(engine, [(sw["points_raw"], sw["ref_from_sensor"], sw["time_lag"]) for sw in s["lidar_sweeps"]])
+    assert np.array_equal(xyzi, ref_xyzi) and np.array_equal(t, ref_t)
+
+
+def test_projection_and_relations_match_oracle(engine):
+    from msc_geom.camera_agent import projection_evidence
+    from msc_geom.scenegraph_agent import SceneGraphAgent
+    s = make_sample(81, n_sweeps=1, n_boxes=200)
+    boxes = boxes_from_annotations(s["annotations"])
+    pose = np.stack([c["ego_pose"] for c in s["cameras"]]); cal = np.stack([c["calib"] for c in s["cameras"]])
+    K = np.stack([c["intrinsic"].reshape(9) for c in s["cameras"]])
+    vis, ext = ops.project_boxes(engine, boxes, pose, cal, K)
+    rv, re = OB.oracle_project(boxes, pose, cal, K)
+    assert np.array_equal(vis, rv) and np.array_equal(ext, re) and vis.sum() > 10
+    ev = projection_evidence(engine, s)
+    assert sum(v["visible_objects"] for v in ev.values()) == int(vis.sum())
+    agent = SceneGraphAgent(object(), "m", "n", engine=engine)
+    for ego in (None, s["ego_pose"]):
+        rel = agent.relations(s["annotations"], ego)
+        ref = OB.oracle_relations(OB.oracle_footprints(boxes, ego))
+        assert np.array_equal(rel["rect"], OB.oracle_footprints(boxes, ego))
+        assert np.array_equal(rel["dist"], ref["dist"]) and np.array_equal(rel["category"], ref["category"]) and np.array_equal(rel["overlap"], ref["overlap"])
+        # bearing goes through atan2 (CUDA vs glibc differ in the last ulps): 1e-5 relative, as north_star states
+        assert np.allclose(rel["bearing"], ref["bearing"], rtol=1e-5, atol=1e-4)
+    assert rel["overlap"].sum() > 200  # diagonal + some genuinely overlapping footprints
+
+
+def test_patch_reference_style_classes(engine, golden_dir):
+    """integration.patch_reference() on stand-ins shaped like the reference classes (same attribute names)."""
+    from msc_geom import integration
+
+    class RefLidar:  # attributes of lidar_agent.py:40-49
+        def __init__(self):
+            self.bev_resolution, self.bev_range, self.dbscan_eps, self.dbscan_min_samples = 800, 50, 0.5, 10
+
+    class RefScene:
+        def __init__(self):
+            self.spatial_zones = {}
+
+    integration.patch_reference(RefLidar, RefScene, engine)
+    g = np.load(os.path.join(golden_dir, "keyframe_mock.npz"))
+    a = RefLidar()
+    kept = a._preprocess_point_cloud(g["points"])
+    ground, obj = a._segment_ground(kept)
+    assert np.array_equal(kept, g["kept"]) and np.array_equal(a._generate_multi_layer_bev(ground, obj)["semantic"], g["semantic"])
+    sg = RefScene()
+    sg.spatial_zones = {z: None for z in ("front_close", "front_medium", "front_far", "left_close", "left_medium", "right_close", "right_medium",
+                                          "back_close", "back_medium")}
+    objs = sg._parse_annotations([{"category_name": "vehicle.car", "translation": [10.0, 2.0, 0.5], "velocity": [3.0, 0.5]}])
+    assert objs[0]["direction"] == "right" and float(objs[0]["distance"]) == 10.198039027185569
+    assert [o["id"] for o in sg._build_spatial_zones(objs)["right_medium"]] == ["obj_0"]
+
+
+def test_bad_arguments_raise(engine):
+    from msc_geom.engine import make_params
+    s = make_sample(90, n_sweeps=1, n_boxes=4)
+    hb = pack_batch([s])
+    with pytest.raises(_capi.MscError):
+        engine.run_fused(engine.upload(hb), params=GeomParams(range_max=80.0))      # fixed-point centroid range
+    with pytest.raises(_capi.MscError):
+        engine.run_fused(engine.upload(hb), params=GeomParams(bev_res=201))          # odd grid
+    with pytest.raises(_capi.MscError):
+        engine.run_fused(engine.upload(hb), params=GeomParams(n_cams=4))             # batch packed for 6 cameras
