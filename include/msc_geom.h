@@ -133,11 +133,12 @@ int msc_aggregate_sweeps(float remove_close_radius, const float* points, int32_t
  * Keyframe path, bit-exact drop-in for LiDARAgent._preprocess_point_cloud + _segment_ground
  * (lidar_agent.py:103-132): order-preserving compaction of the kept rows into `kept` and of the ground /
  * object subsets.  pts has `pitch` floats per row (4 mock loader, 5 devkit view, nuscenes_loader.py:152-155);
- * outputs are dense (n,4).  counts (device u32[3]) = n_kept, n_ground, n_object.
+ * outputs are dense (n,4).  counts (device u32[3]) = n_kept, n_ground, n_object.  split_only != 0 skips the range/height
+ * gate: that is _segment_ground on its own (every row is kept; rows whose z is NaN land in `object`, like pc[~mask]).
  */
-int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32_t n, int32_t pitch, float* kept,
-                              float* ground, float* object, uint32_t* counts, uint32_t* scratch, size_t scratch_elems,
-                              void* stream);
+int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32_t n, int32_t pitch, int32_t split_only,
+                              float* kept, float* ground, float* object, uint32_t* counts, uint32_t* scratch,
+                              size_t scratch_elems, void* stream);
 
 /*
  * Keyframe BEV raster layers, bit-exact for the pre-overlay half of LiDARAgent._generate_multi_layer_bev

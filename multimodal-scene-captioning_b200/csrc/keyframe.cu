@@ -22,22 +22,23 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 }
 
 // lidar_agent.py:106-110 (float32, separate roundings, strict compares) and :128
-__device__ __forceinline__ uint32_t keyframe_class(const float* __restrict__ p, const msc_params& P) {
+// split_only: _segment_ground alone (no gate; a NaN z compares false and lands in `object`, like pc[~mask])
+__device__ __forceinline__ uint32_t keyframe_class(const float* __restrict__ p, const msc_params& P, bool split_only) {
     const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])));
-    const bool ok = (d > P.range_min) && (d < P.range_max) && (p[2] < P.z_max) && (p[2] > P.z_min);
+    const bool ok = split_only || ((d > P.range_min) && (d < P.range_max) && (p[2] < P.z_max) && (p[2] > P.z_min));
     if (!ok) return 0u;
     return (p[2] < P.ground_z) ? 1u : 2u;  // 1 ground, 2 object
 }
 
 // pass 1: per-block counts of kept / ground / object rows
 __global__ void __launch_bounds__(kCompactThreads) kf_count_kernel(const __grid_constant__ msc_params P, const float* __restrict__ pts,
-                                                                  uint32_t n, int pitch, uint32_t* __restrict__ block_counts) {
+                                                                  uint32_t n, int pitch, bool split_only, uint32_t* __restrict__ block_counts) {
     __shared__ uint32_t s_cnt[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * kCompactThreads + threadIdx.x;
     uint32_t cls = 0;
-    if (i < n) cls = keyframe_class(pts + (size_t)i * pitch, P);
+    if (i < n) cls = keyframe_class(pts + (size_t)i * pitch, P, split_only);
     const uint32_t g = __popc(__ballot_sync(0xffffffffu, cls == 1u));
     const uint32_t o = __popc(__ballot_sync(0xffffffffu, cls == 2u));
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], g); atomicAdd(&s_cnt[1], o); }
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(1024) kf_scan_kernel(uint32_t* __restrict__ bl
 // pass 3: ordered scatter.  Within a block, ranks come from warp ballots + a warp-offset scan, so row order is
 // exactly the input order (boolean-mask indexing, lidar_agent.py:112,129-130).
 __global__ void __launch_bounds__(kCompactThreads) kf_scatter_kernel(const __grid_constant__ msc_params P, const float* __restrict__ pts,
-                                                                    uint32_t n, int pitch, const uint32_t* __restrict__ block_offsets,
+                                                                    uint32_t n, int pitch, bool split_only, const uint32_t* __restrict__ block_offsets,
                                                                     float* __restrict__ kept, float* __restrict__ ground,
                                                                     float* __restrict__ object) {
     __shared__ uint32_t s_w[2][32];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kCompactThreads) kf_scatter_kernel(const __gri
     float4 row = make_float4(0, 0, 0, 0);
     if (i < n) {
         const float* p = pts + (size_t)i * pitch;
-        cls = keyframe_class(p, P);
+        cls = keyframe_class(p, P, split_only);
         row = make_float4(p[0], p[1], p[2], p[3]);
     }
     const uint32_t bg = __ballot_sync(0xffffffffu, cls == 1u), bo = __ballot_sync(0xffffffffu, cls == 2u);
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(kCompactThreads) agg_scatter_kernel(float rc, 
 
 extern "C" {
 
-int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32_t n, int32_t pitch, float* kept, float* ground,
-                              float* object, uint32_t* counts, uint32_t* scratch, size_t scratch_elems, void* stream_v) {
+int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32_t n, int32_t pitch, int32_t split_only, float* kept,
+                              float* ground, float* object, uint32_t* counts, uint32_t* scratch, size_t scratch_elems, void* stream_v) {
     using namespace msc;
     MSC_REQUIRE(params && counts && scratch, "null argument");
     MSC_REQUIRE(pitch >= 4, "pitch must be >= 4 floats");
@@ -329,9 +330,9 @@ int msc_keyframe_filter_split(const msc_params* params, const float* pts, uint32
     MSC_REQUIRE(scratch_elems >= (size_t)n_blocks * 2 + 2, "scratch too small: need %zu u32", (size_t)n_blocks * 2 + 2);
     if (n == 0) { MSC_CUDA(cudaMemsetAsync(counts, 0, 3 * sizeof(uint32_t), stream)); return MSC_OK; }
     MSC_REQUIRE(pts && kept && ground && object, "null buffer");
-    kf_count_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(*params, pts, n, pitch, scratch);
+    kf_count_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(*params, pts, n, pitch, split_only != 0, scratch);
     kf_scan_kernel<<<1, 1024, 0, stream>>>(scratch, n_blocks, counts);
-    kf_scatter_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(*params, pts, n, pitch, scratch, kept, ground, object);
+    kf_scatter_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(*params, pts, n, pitch, split_only != 0, scratch, kept, ground, object);
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
 }

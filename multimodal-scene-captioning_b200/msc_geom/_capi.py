@@ -55,7 +55,7 @@ _PROTOS = {
     "msc_fused_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
     "msc_aggregate_sweeps": (C.c_int, [C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "msc_keyframe_filter_split": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p,
+    "msc_keyframe_filter_split": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "msc_keyframe_bev": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -83,15 +83,28 @@ def sqrt_thresholds(lo: float, hi: float):
     sqrt is correctly rounded and monotonic, so the predicate is identical to the reference's
     `distances > lo` / `distances < hi` (lidar_agent.py:106-107)."""
     lo32, hi32 = np.float32(lo), np.float32(hi)
-    s = np.float32(lo32 * lo32)
-    while np.sqrt(s) > lo32:
-        s = np.nextafter(s, np.float32(-np.inf))
-    while not (np.sqrt(s) > lo32):
-        s = np.nextafter(s, np.float32(np.inf))
-    s_lo = s
-    s = np.float32(hi32 * hi32)
-    while np.sqrt(s) < hi32:
-        s = np.nextafter(s, np.float32(np.inf))
-    while not (np.sqrt(s) < hi32):
-        s = np.nextafter(s, np.float32(-np.inf))
-    return float(s_lo), float(s)
+
+    def first_true(pred):
+        """Smallest non-negative float32 (by bit pattern, which orders non-negative floats) satisfying a monotone predicate."""
+        a, b = 0, 0x7F800000  # +0.0 .. +inf
+        if not pred(np.uint32(b).view(np.float32)):
+            return None
+        while a < b:
+            m = (a + b) // 2
+            if pred(np.uint32(m).view(np.float32)):
+                b = m
+            else:
+                a = m + 1
+        return np.uint32(a).view(np.float32)
+
+    with np.errstate(invalid="ignore"):
+        s_lo = first_true(lambda s: np.sqrt(s) > lo32)          # monotone: false ... true
+        above = first_true(lambda s: not (np.sqrt(s) < hi32))   # first s that is NOT below the upper limit
+    s_lo = np.float32(np.inf) if s_lo is None else s_lo
+    if above is None:
+        s_hi = np.float32(np.inf)
+    elif above.view(np.uint32) == 0:
+        s_hi = np.float32(-1.0)  # nothing passes
+    else:
+        s_hi = np.uint32(above.view(np.uint32) - 1).view(np.float32)
+    return float(s_lo), float(s_hi)

@@ -103,10 +103,7 @@ class LiDARAgent:
         return ops.keyframe_filter_split(self.engine, pc, self._params())[0]
 
     def _segment_ground(self, pc: np.ndarray, ground_threshold: float = -1.4) -> Tuple[np.ndarray, np.ndarray]:
-        # the split of an already filtered cloud: run the same kernel with the range/height gates wide open
-        p = self._params(ground_threshold)
-        p.range_min, p.range_max, p.z_min, p.z_max = -1.0, float("inf"), -float("inf"), float("inf")
-        _, ground, obj = ops.keyframe_filter_split(self.engine, pc, p)
+        _, ground, obj = ops.keyframe_filter_split(self.engine, pc, self._params(ground_threshold), split_only=True)
         return ground, obj
 
     def _generate_multi_layer_bev(self, ground_points: np.ndarray, object_points: np.ndarray) -> Dict[str, np.ndarray]:

@@ -42,7 +42,7 @@ def _raw_rows(pc: np.ndarray) -> Tuple[np.ndarray, int]:
     return np.ascontiguousarray(pc), pc.shape[1]
 
 
-def keyframe_filter_split(eng: GeometryEngine, pc: np.ndarray, params: Optional[GeomParams] = None):
+def keyframe_filter_split(eng: GeometryEngine, pc: np.ndarray, params: Optional[GeomParams] = None, split_only: bool = False):
     """LiDARAgent._preprocess_point_cloud + _segment_ground (lidar_agent.py:103-132): kept, ground, object as (n,4) f32."""
     p = params or GeomParams(bev_res=800)
     rows, pitch = _raw_rows(pc)
@@ -59,7 +59,7 @@ def keyframe_filter_split(eng: GeometryEngine, pc: np.ndarray, params: Optional[
     n_blocks = (n + 1023) // 1024
     scratch = torch.empty(n_blocks * 2 + 2, dtype=torch.int32, device=d)
     mp = make_params(p)
-    _capi.check(eng.lib.msc_keyframe_filter_split(C.byref(mp), src.data_ptr(), n, pitch, kept.data_ptr(), ground.data_ptr(), obj.data_ptr(),
+    _capi.check(eng.lib.msc_keyframe_filter_split(C.byref(mp), src.data_ptr(), n, pitch, int(split_only), kept.data_ptr(), ground.data_ptr(), obj.data_ptr(),
                                                   counts.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(eng)), "msc_keyframe_filter_split")
     eng.kernel_launches += 3
     nk, ng, no = (int(v) for v in counts.cpu().tolist())

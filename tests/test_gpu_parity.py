@@ -184,6 +184,19 @@ def test_keyframe_filter_split_and_bev_match_reference(engine, golden_dir, name)
         assert bev[k].dtype == g[k].dtype and np.array_equal(bev[k], g[k]), (name, k)
 
 
+def test_segment_ground_alone_keeps_every_row(engine):
+    """_segment_ground on an arbitrary array (lidar_agent.py:128-130): no gate, NaN z goes to `object` like pc[~mask]."""
+    from msc_geom.lidar_agent import LiDARAgent
+    rng = np.random.default_rng(9)
+    pc = rng.normal(0, 40, (5000, 4)).astype(np.float32)
+    pc[::50, 2] = np.nan; pc[1::50, 0] = np.inf; pc[2::50, 2] = -1.4; pc[3::50, 2] = np.float32(-1.4000001)
+    agent = LiDARAgent(object(), "m", "n", engine=engine)
+    for thr in (-1.4, 0.25):
+        ground, obj = agent._segment_ground(pc, thr)
+        m = pc[:, 2] < thr
+        assert np.array_equal(ground, pc[m], equal_nan=True) and np.array_equal(obj, pc[~m], equal_nan=True)
+
+
 def test_keyframe_strided_devkit_view(engine, golden_dir):
     g = np.load(os.path.join(golden_dir, "keyframe_synth.npz"))
     raw = np.zeros((g["points"].shape[0], 5), np.float32)

@@ -76,6 +76,28 @@ def test_params_defaults_follow_reference():
     assert p.centroid_shift == 17 and GeomParams(range_max=20.0).centroid_shift == 17 and p.intensity_shift == 8
 
 
+@pytest.mark.parametrize("lo,hi", [(1.0, 50.0), (0.0, 30.0), (-1.0, float("inf")), (2.5, 64.0), (1e-3, 1e3), (5.0, 5.0), (7.0, 3.0)])
+def test_sqrt_thresholds_general(lo, hi):
+    s_lo, s_hi = G.sqrt_thresholds(lo, hi)
+    s = np.concatenate([np.float32([0.0, 1e-30, lo * lo, hi * hi if np.isfinite(hi) else 1e30, 3e38, np.inf, np.nan]),
+                        np.random.default_rng(2).uniform(0, 5000, 50000).astype(np.float32)])
+    for v in (lo * lo, hi * hi):
+        if np.isfinite(v) and v > 0:
+            b = np.float32(v)
+            ring = [b]
+            for _ in range(64):
+                ring += [np.nextafter(ring[-1], np.float32(np.inf))]
+            ring2 = [b]
+            for _ in range(64):
+                ring2 += [np.nextafter(ring2[-1], np.float32(0))]
+            s = np.concatenate([s, np.float32(ring + ring2)])
+    with np.errstate(invalid="ignore"):
+        d = np.sqrt(s)
+        want = (d > np.float32(lo)) & (d < np.float32(hi))
+        got = (s >= np.float32(s_lo)) & (s <= np.float32(s_hi))
+    assert np.array_equal(want, got)
+
+
 @pytest.mark.parametrize("n,world", [(404, 8), (34149, 8), (5, 8), (0, 2), (592, 1)])
 def test_shard_range_partitions(n, world):
     spans = [shard_range(n, r, world) for r in range(world)]
