@@ -147,7 +147,7 @@ def main():
             return 0
         n_unique = min(args.unique, 8)
         hb = pack_batch([make_sample(i, **wkw) for i in range(n_unique)])
-        per_step = args.cpu_samples or max(cores, 8)
+        per_step = args.cpu_samples or 4 * cores
         for _ in range(max(args.warmup, 1) if args.warmup else 0):
             cpu_oracle_throughput(hb, params, max(cores, 2), cores)
         t0 = time.perf_counter()

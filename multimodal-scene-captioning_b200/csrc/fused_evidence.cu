@@ -171,7 +171,7 @@ __device__ void compute_wedge(int image_w, const double* __restrict__ lcal, cons
     wq[5] = (float)((Rl[1] * re[0] + Rl[4] * re[1]) + Rl[7] * re[2]);
 }
 
-// grid: ceil(max(n_boxes_total * max(n_cams,1), n_samples * cull_cells) / 256) blocks of 256 threads
+// grid: ceil(max(n_boxes_total, n_samples) * max(n_cams,1) / 256) blocks of 256 threads
 __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
                                                           unsigned char* __restrict__ ws) {
     const msc_params& P = A.P;
@@ -219,34 +219,39 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
                     A.in.cam_calib + ((size_t)sample * n_cams + c) * 7, A.in.cam_K + ((size_t)sample * n_cams + c) * 9, (double)P.image_w,
                     (double)P.image_h, A.out.proj_visible + gid, A.out.proj_extent + (size_t)gid * 4);
     }
-    // (3) wedge classes per (sample, cull cell); the wedge of every camera is recomputed per thread from the
-    //     sample's calibration (cheap next to one kernel-wide dependency)
-    const int ncc = A.L.cull_dim * A.L.cull_dim;
-    if (n_cams > 0 && gid < A.in.n_samples * ncc) {
-        const int sample = gid / ncc, i = gid - sample * ncc;
-        const int gy = i / A.L.cull_dim, gx = i - gy * A.L.cull_dim;
-        const float cell_m = (A.two_r / A.resf) * (float)(1 << A.L.cull_shift);
-        const int last = A.L.cull_dim - 1;
-        const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
-        // edge cells absorb everything clipped into them
-        const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
-        const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
-        const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
-        const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
-        uint32_t bits = 0;
-        for (int c = 0; c < n_cams; ++c) {
-            float wq[6];
-            compute_wedge(P.image_w, A.in.lidar_calib + (size_t)sample * 7, A.in.cam_calib + ((size_t)sample * n_cams + c) * 7,
-                          A.in.cam_K + ((size_t)sample * n_cams + c) * 9, wq);
-            if (i == 0) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) wedges[((size_t)sample * MSC_MAX_CAMS + c) * 6 + k] = wq[k];
-            }
-            const uint32_t k = classify_cell(wq, x0, x1, y0, y1);
-            bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
-        }
-        fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
+    // (3) camera wedges: one thread per (sample, camera)
+    if (n_cams > 0 && gid < A.in.n_samples * n_cams) {
+        const int sample = gid / n_cams, c = gid - sample * n_cams;
+        compute_wedge(P.image_w, A.in.lidar_calib + (size_t)sample * 7, A.in.cam_calib + ((size_t)sample * n_cams + c) * 7,
+                      A.in.cam_K + ((size_t)sample * n_cams + c) * 9, wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6);
     }
+}
+
+// wedge classes per (sample, cull cell), from the wedges the table kernel wrote (launched after it on the same stream)
+__global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
+    const msc_params& P = A.P;
+    const int n_cams = P.n_cams;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* const wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
+    uint16_t* const fovcls = reinterpret_cast<uint16_t*>(ws + T.fovcls_off);
+    const int ncc = A.L.cull_dim * A.L.cull_dim;
+    if (gid >= A.in.n_samples * ncc) return;
+    const int sample = gid / ncc, i = gid - sample * ncc;
+    const int gy = i / A.L.cull_dim, gx = i - gy * A.L.cull_dim;
+    const float cell_m = (A.two_r / A.resf) * (float)(1 << A.L.cull_shift);
+    const int last = A.L.cull_dim - 1;
+    const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
+    // edge cells absorb everything clipped into them
+    const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
+    const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
+    const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
+    const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
+    uint32_t bits = 0;
+    for (int c = 0; c < n_cams; ++c) {
+        const uint32_t k = classify_cell(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
+        bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
+    }
+    fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
 }
 
 // ------------------------------------------------------------------------------------------------ streaming kernel
@@ -725,10 +730,16 @@ static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* 
     g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
     // (1) tables: prepared boxes, projection, wedges, wedge classes
     const int ncc = args.L.cull_dim * args.L.cull_dim;
-    long long work = (long long)n_boxes_total * (args.P.n_cams > 0 ? args.P.n_cams : 1);
-    if ((long long)args.in.n_samples * ncc > work) work = (long long)args.in.n_samples * ncc;
+    const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
+    long long work = (long long)n_boxes_total * cams;
+    if ((long long)args.in.n_samples * cams > work) work = (long long)args.in.n_samples * cams;
     if (work > 0) {
         fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
+        MSC_CUDA(cudaGetLastError());
+    }
+    if (fov) {
+        const long long cells = (long long)args.in.n_samples * ncc;
+        fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
     }
     // (2) the streaming pass

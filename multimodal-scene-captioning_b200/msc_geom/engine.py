@@ -144,7 +144,7 @@ class GeometryEngine:
             ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
         _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
                                                       C.c_void_p(stream)), "msc_fused_evidence_batch")
-        self.kernel_launches += 2  # table kernel + streaming kernel
+        self.kernel_launches += 3 if _capi.get_option("fov") else 2  # tables (+ wedge classes) + streaming kernel
         return out
 
     def process_samples(self, samples: Sequence[dict], params: Optional[GeomParams] = None) -> Dict[str, np.ndarray]:
