@@ -179,6 +179,16 @@ int msc_project_boxes(int32_t n_boxes, const double* boxes, int32_t n_cams, cons
 int msc_cluster_aabb(const float* pts, uint32_t n, int32_t pitch, const int32_t* labels, int32_t n_clusters,
                      float* out11, void* stream);
 
+/* Per-cluster 4-view raster the reference sends to its VLM (LiDARAgent._generate_cluster_visualization,
+ * lidar_agent.py:241-356), points only (axes / titles / mosaic are drawn on the host afterwards).
+ * pts_xyzi: dense (n,4) object points; order: point indices grouped by cluster, original order inside a cluster;
+ * cluster_off: [n_clusters+1] offsets into order; center_scale: [n_clusters,4] f32 = cluster mean (:255) and scale (:264),
+ * computed on the host with the reference's own arithmetic; keys: scratch u32 [n_clusters,512,512]; irange: scratch
+ * u32 [n_clusters,4,2]; out_bgr: u8 [n_clusters,512,512,3]. */
+int msc_cluster_views(const float* pts_xyzi, const uint32_t* order, const int32_t* cluster_off, int32_t n_clusters,
+                      int32_t max_cluster_points, const float* center_scale, uint32_t* keys, uint32_t* irange, uint8_t* out_bgr,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -828,6 +828,9 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     switch (g_opt_config) {
         case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 3: return dispatch_fused<Cfg<512, 4, 2>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 4: return dispatch_fused<Cfg<768, 2, 3, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 5: return dispatch_fused<Cfg<1024, 1, 4, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         default: return dispatch_fused<Cfg<512, 2, 4>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
     }
 }

@@ -14,7 +14,7 @@ from . import lidar_agent as _la
 from . import scenegraph_agent as _sg
 from .engine import GeometryEngine
 
-_LIDAR_METHODS = ("_preprocess_point_cloud", "_segment_ground", "_generate_multi_layer_bev")
+_LIDAR_METHODS = ("_preprocess_point_cloud", "_segment_ground", "_generate_multi_layer_bev", "_generate_cluster_visualization")
 _SCENE_METHODS = ("_parse_annotations", "_build_spatial_zones")
 
 

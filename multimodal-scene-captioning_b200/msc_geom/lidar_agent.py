@@ -76,6 +76,38 @@ def finish_bev_layers(count: np.ndarray, height: np.ndarray, semantic: np.ndarra
     return {"semantic": vis, "height": height, "density": density}
 
 
+def finish_cluster_view(grid: np.ndarray, img_size: int = 256) -> np.ndarray:
+    """Host half of _generate_cluster_visualization: axes and titles (lidar_agent.py:299-313, :353-354) on top of the GPU
+    disc raster.  They sit well inside their quadrant, a disc bleeds at most two pixels over a quadrant border, so drawing
+    them after all discs gives the reference's image."""
+    import cv2
+    grid = np.ascontiguousarray(grid)
+    half = img_size // 2
+    for qx, qy, title in ((0, 0, "Top (XY)"), (1, 0, "Side (XZ)"), (0, 1, "Front (YZ)"), (1, 1, "3D View")):
+        ox, oy = qx * img_size, qy * img_size
+        if (qx, qy) != (1, 1):
+            cv2.line(grid, (ox + half, oy + half), (ox + half + 30, oy + half), (0, 0, 255), 2)   # x axis, red
+            cv2.line(grid, (ox + half, oy + half), (ox + half, oy + half - 30), (0, 255, 0), 2)   # y axis, green
+        cv2.putText(grid, title, (ox + 10, oy + 20), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 0, 0), 1)
+    return grid
+
+
+def cluster_mosaic(images: List[np.ndarray]) -> np.ndarray:
+    """The batch image of _classify_batch_with_llm (lidar_agent.py:366-386): up to three columns, '#idx' labels."""
+    import cv2
+    if len(images) == 1:
+        return images[0]
+    cols = min(3, len(images))
+    rows = (len(images) + cols - 1) // cols
+    h, w = images[0].shape[:2]
+    sheet = np.full((rows * h, cols * w, 3), 255, dtype=np.uint8)
+    for idx, img in enumerate(images):
+        r, c = divmod(idx, cols)
+        sheet[r * h:(r + 1) * h, c * w:(c + 1) * w] = img
+        cv2.putText(sheet, f"#{idx}", (c * w + 10, r * h + 50), cv2.FONT_HERSHEY_SIMPLEX, 1.5, (255, 0, 0), 3)
+    return sheet
+
+
 class LiDARAgent:
     def __init__(self, client, model: str, agent_name: str, engine: Optional[GeometryEngine] = None,
                  llm: Optional[Callable[..., str]] = None, cluster_classifier: Optional[Callable[[List[dict]], List[dict]]] = None):
@@ -110,6 +142,17 @@ class LiDARAgent:
         res, r = int(self.bev_resolution), self.bev_range
         count, height, sem = ops.keyframe_bev_layers(self.engine, ground_points, object_points, res, float(r))
         return finish_bev_layers(count, height, sem, res, r)
+
+    def _generate_cluster_visualization(self, points: np.ndarray, img_size: int = 256) -> np.ndarray:
+        """One cluster -> 512x512 4-view image (lidar_agent.py:241-356)."""
+        if img_size != 256:
+            raise ValueError("the device raster is built for the reference's img_size = 256")
+        return finish_cluster_view(ops.cluster_views(self.engine, points, [np.arange(len(points))])[0])
+
+    def _cluster_visualizations(self, object_points: np.ndarray, labels: np.ndarray, order: List[int]) -> List[np.ndarray]:
+        """All clusters of a cloud in one launch (the reference loops over clusters, lidar_agent.py:198-209)."""
+        discs = ops.cluster_views(self.engine, object_points, [np.nonzero(labels == l)[0] for l in order])
+        return [finish_cluster_view(d) for d in discs]
 
     def _cluster_metadata(self, object_points: np.ndarray, labels: np.ndarray, order: List[int]) -> List[dict]:
         n_clusters = int(labels.max()) + 1 if labels.size else 0

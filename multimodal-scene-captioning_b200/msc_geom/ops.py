@@ -197,3 +197,39 @@ def aggregate_sweeps(eng: GeometryEngine, sweeps, remove_close_radius: float = 1
     eng.kernel_launches += 3
     m = int(n_out.item())
     return out[:m].cpu().numpy(), out_t[:m].cpu().numpy()
+
+
+def cluster_views(eng: GeometryEngine, points: np.ndarray, clusters) -> np.ndarray:
+    """Point discs of LiDARAgent._generate_cluster_visualization (lidar_agent.py:241-351) for a list of clusters of one cloud.
+    points: (N,4) f32; clusters: list of index arrays into points (original order inside a cluster).  Returns u8
+    [K,512,512,3] without axes / titles (see lidar_agent.finish_cluster_view).  The cluster mean and pixel scale are
+    evaluated on the host with NumPy exactly as the reference does (:255-264) -- a few hundred floats per cluster."""
+    K = len(clusters)
+    if K == 0:
+        return np.zeros((0, 512, 512, 3), np.uint8)
+    d = eng.device
+    pts = np.ascontiguousarray(points[:, :4], np.float32)
+    cs = np.zeros((K, 4), np.float32)
+    off = np.zeros(K + 1, np.int32)
+    for k, idx in enumerate(clusters):
+        cp = pts[idx, :3]
+        center = cp.mean(axis=0)
+        centered = cp - center
+        max_range = max(centered[:, 0].max() - centered[:, 0].min(), centered[:, 1].max() - centered[:, 1].min(),
+                        centered[:, 2].max() - centered[:, 2].min())
+        cs[k, :3] = center
+        cs[k, 3] = (256 * 0.35) / max_range if max_range > 0 else 1
+        off[k + 1] = off[k] + len(idx)
+    order = np.concatenate([np.asarray(i, np.int64) for i in clusters]).astype(np.uint32)
+    t_pts = torch.from_numpy(pts).to(d)
+    t_order = torch.from_numpy(order.view(np.int32)).to(d)
+    t_off = torch.from_numpy(off).to(d)
+    t_cs = torch.from_numpy(cs).to(d)
+    keys = torch.empty((K, 512, 512), dtype=torch.int32, device=d)
+    irange = torch.empty((K, 4, 2), dtype=torch.int32, device=d)
+    out = torch.empty((K, 512, 512, 3), dtype=torch.uint8, device=d)
+    max_n = int(np.diff(off).max())
+    _capi.check(eng.lib.msc_cluster_views(t_pts.data_ptr(), t_order.data_ptr(), t_off.data_ptr(), K, max_n, t_cs.data_ptr(), keys.data_ptr(),
+                                          irange.data_ptr(), out.data_ptr(), _stream(eng)), "msc_cluster_views")
+    eng.kernel_launches += 2
+    return out.cpu().numpy()

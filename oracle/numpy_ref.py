@@ -299,3 +299,86 @@ def devkit_box_in_image(c, R, wlh, K, imsize=(1600, 900)):
     if not ok:
         return False, np.zeros(4)
     return True, np.array([max(uv[0].min(), 0), max(uv[1].min(), 0), min(uv[0].max(), imsize[0]), min(uv[1].max(), imsize[1])])
+
+
+# ----------------------------------------------------------------------------------------------------
+# cluster 4-view raster and batch mosaic
+# ----------------------------------------------------------------------------------------------------
+_CIRCLE_R2 = [(dx, dy) for dy in range(-2, 3) for dx in range(-(2 - abs(dy)), 2 - abs(dy) + 1)]  # cv2.circle(r=2, filled)
+
+
+def cluster_view_params(points: np.ndarray, img_size: int = 256):
+    """lidar_agent.py:255-264: cluster mean (float32, NumPy's own reduction) and the pixel scale."""
+    center = points[:, :3].mean(axis=0)
+    centered = points[:, :3] - center
+    max_range = max(centered[:, 0].max() - centered[:, 0].min(), centered[:, 1].max() - centered[:, 1].min(),
+                    centered[:, 2].max() - centered[:, 2].min())
+    scale = (img_size * 0.35) / max_range if max_range > 0 else 1
+    return center, centered, scale
+
+
+def cluster_view_points(points: np.ndarray, img_size: int = 256) -> np.ndarray:
+    """Point discs of _generate_cluster_visualization (lidar_agent.py:267-351) without cv2: white 2x2 grid, per view the
+    points in array order, each a filled radius-2 circle in the view-normalised intensity grey."""
+    _, centered, scale = cluster_view_params(points, img_size)
+    grid = np.ones((img_size * 2, img_size * 2, 3), dtype=np.uint8) * 255
+
+    def splat(px, py, valid, qx, qy):
+        px, py = px[valid], py[valid]
+        inten = points[valid, 3]
+        inten = ((inten - inten.min()) / (inten.max() - inten.min() + 1e-6) * 255).astype(np.uint8)
+        for x, y, g in zip(px, py, inten):
+            cx, cy = qx * img_size + x, qy * img_size + img_size - y - 1
+            for dx, dy in _CIRCLE_R2:
+                xx, yy = cx + dx, cy + dy
+                if 0 <= xx < 2 * img_size and 0 <= yy < 2 * img_size:
+                    grid[yy, xx] = g
+
+    for (a1, a2, qx, qy) in ((0, 1, 0, 0), (0, 2, 1, 0), (1, 2, 0, 1)):
+        px = (centered[:, a1] * scale + img_size / 2).astype(int)
+        py = (centered[:, a2] * scale + img_size / 2).astype(int)
+        splat(px, py, (px >= 0) & (px < img_size) & (py >= 0) & (py < img_size), qx, qy)
+    ang = np.pi / 6
+    rot_x = np.array([[1, 0, 0], [0, np.cos(ang), -np.sin(ang)], [0, np.sin(ang), np.cos(ang)]])
+    rot_y = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    rot = centered @ rot_x.T @ rot_y.T
+    ix = ((rot[:, 0] + rot[:, 1] * 0.5) * scale + img_size / 2).astype(int)
+    iy = ((rot[:, 2] - rot[:, 1] * 0.5) * scale + img_size / 2).astype(int)
+    splat(ix, iy, (ix >= 0) & (ix < img_size) & (iy >= 0) & (iy < img_size), 1, 1)
+    return grid
+
+
+def cluster_view_overlays(grid: np.ndarray, img_size: int = 256) -> np.ndarray:
+    """Axes and titles (lidar_agent.py:299-313, :353-354).  Drawn after all discs: a disc bleeds at most 2 px over a
+    quadrant border, the overlays sit >= 10 px inside their quadrant, so the reference's interleaved order gives the same image."""
+    import cv2
+    grid = np.ascontiguousarray(grid)
+    for (qx, qy, title) in ((0, 0, "Top (XY)"), (1, 0, "Side (XZ)"), (0, 1, "Front (YZ)")):
+        ox, oy, c = qx * img_size, qy * img_size, img_size // 2
+        cv2.line(grid, (ox + c, oy + c), (ox + c + 30, oy + c), (0, 0, 255), 2)
+        cv2.line(grid, (ox + c, oy + c), (ox + c, oy + c - 30), (0, 255, 0), 2)
+        cv2.putText(grid, title, (ox + 10, oy + 20), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 0, 0), 1)
+    cv2.putText(grid, "3D View", (img_size + 10, img_size + 20), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (0, 0, 0), 1)
+    return grid
+
+
+def generate_cluster_visualization(points: np.ndarray, img_size: int = 256) -> np.ndarray:
+    """lidar_agent.py:241-356"""
+    return cluster_view_overlays(cluster_view_points(points, img_size), img_size)
+
+
+def cluster_mosaic(images) -> np.ndarray:
+    """lidar_agent.py:366-386: up to three columns, '#idx' labels; a single image is passed through."""
+    import cv2
+    if len(images) == 1:
+        return images[0]
+    n = len(images)
+    cols = min(3, n)
+    rows = (n + cols - 1) // cols
+    h, w = images[0].shape[:2]
+    out = np.ones((rows * h, cols * w, 3), dtype=np.uint8) * 255
+    for idx, img in enumerate(images):
+        r, c = idx // cols, idx % cols
+        out[r * h:(r + 1) * h, c * w:(c + 1) * w] = img
+        cv2.putText(out, f"#{idx}", (c * w + 10, r * h + 50), cv2.FONT_HERSHEY_SIMPLEX, 1.5, (255, 0, 0), 3)
+    return out

@@ -74,6 +74,28 @@ def main():
                         num_points=np.array([m["num_points"] for m in meta], np.int64),
                         direction=np.array([m["direction"] for m in meta]))
     print("clusters", len(meta), "detected", len(objs))
+    # (5b) cluster 4-view rasters and the batch mosaic, straight from the reference
+    ref_agent = LiDARAgent(object(), "m", "n")
+    rng = np.random.default_rng(7)
+    view_clusters = [obj[labels == l] for l in sorted(set(labels.tolist()) - {-1})[:3]]
+    car = rng.uniform(-0.5, 0.5, (900, 3)) * np.array([4.6, 1.9, 1.7]) + np.array([12.0, -3.0, -1.0])
+    view_clusters.append(np.concatenate([car, rng.integers(0, 255, (900, 1))], 1).astype(np.float32))     # dense box-shaped cluster
+    view_clusters.append(np.tile(np.array([[5.0, 5.0, 0.5, 10.0]], np.float32), (6, 1)))                  # all points identical: max_range == 0
+    line = np.zeros((40, 4), np.float32); line[:, 0] = np.linspace(-3, 3, 40); line[:, 3] = 77.0         # constant intensity, thin line
+    view_clusters.append(line)
+    views = [ref_agent._generate_cluster_visualization(c) for c in view_clusters]
+    captured_img = {}
+    import agents.content_transform.lidar_agent as _la_mod
+    ref_agent._image_to_base64 = lambda img: captured_img.setdefault("mosaic", img.copy()) is None or "b64"
+    ref_agent.call_llm = lambda *a, **k: "{}"
+    try:
+        ref_agent._classify_batch_with_llm(views[:5], [{"index": i, "center": np.zeros(3), "dimensions": np.ones(3), "distance": 1.0,
+                                                        "direction": "front", "num_points": 5} for i in range(5)])
+    except Exception as e:  # the stubbed reply is not a classification; the mosaic is captured before it is parsed
+        print("classify stub:", type(e).__name__)
+    np.savez_compressed(os.path.join(HERE, "cluster_views.npz"), n=len(view_clusters), mosaic=captured_img["mosaic"],
+                        **{f"pts_{i}": c for i, c in enumerate(view_clusters)}, **{f"img_{i}": v for i, v in enumerate(views)})
+    print("cluster views", [v.shape for v in views], captured_img["mosaic"].shape)
     angles = np.concatenate([np.arange(0, 360, 7.5), [22.5, 67.5, 112.5, 157.5, 202.5, 247.5, 292.5, 337.5, 359.999]])
     dirs = [agent._get_direction(np.array([np.cos(np.deg2rad(a)), np.sin(np.deg2rad(a))], np.float32) * np.float32(12.5)) for a in angles]
 

@@ -238,6 +238,28 @@ def test_cluster_metadata_matches_reference(engine, golden_dir):
         assert m["distance"] == g["distance"][i] and m["num_points"] == g["num_points"][i] and m["direction"] == str(g["direction"][i])
 
 
+def test_cluster_views_match_reference(engine, golden_dir):
+    """Cluster 4-view raster (lidar_agent.py:241-356) and mosaic (:366-386): exact uint8 equality with the reference's images."""
+    from msc_geom.lidar_agent import LiDARAgent, cluster_mosaic
+    g = np.load(os.path.join(golden_dir, "cluster_views.npz"))
+    agent = LiDARAgent(object(), "m", "n", engine=engine)
+    n = int(g["n"])
+    singles = [agent._generate_cluster_visualization(g[f"pts_{i}"]) for i in range(n)]
+    for i in range(n):
+        assert singles[i].dtype == np.uint8 and np.array_equal(singles[i], g[f"img_{i}"]), i
+    # all clusters of one cloud in a single launch
+    pts = np.concatenate([g[f"pts_{i}"] for i in range(n)])
+    labels = np.concatenate([np.full(len(g[f"pts_{i}"]), i) for i in range(n)])
+    perm = np.random.default_rng(0).permutation(len(pts))          # interleave clusters; order inside a cluster must survive
+    perm = perm[np.argsort(labels[perm] * 0, kind="stable")]
+    inv = np.argsort(perm, kind="stable")
+    keep_order = np.argsort(np.stack([labels, np.arange(len(pts))], 1)[:, 0], kind="stable")
+    batch = agent._cluster_visualizations(pts, labels, list(range(n)))
+    for i in range(n):
+        assert np.array_equal(batch[i], g[f"img_{i}"]), i
+    assert np.array_equal(cluster_mosaic(singles[:5]), g["mosaic"])
+
+
 @pytest.mark.parametrize("case", ["mock", "docs_scene_1", "docs_scene_2", "docs_scene_3", "edge"])
 def test_scenegraph_agent_matches_reference(engine, golden_json, case):
     from msc_geom.scenegraph_agent import SceneGraphAgent

@@ -137,3 +137,15 @@ def test_describe_point_cloud(golden_dir, golden_json):
     mean = np.sqrt(pts[:, 0] ** 2 + pts[:, 1] ** 2).mean()
     assert abs(acc / len(pts) - mean) <= 1e-5 * mean
     assert f"{acc / len(pts):.1f} m" in golden_json["describe_point_cloud_mock"]
+
+
+def test_cluster_views_match_reference(golden_dir):
+    """the NumPy restatement of _generate_cluster_visualization (lidar_agent.py:241-356) and of
+    the batch mosaic (:366-386) against images produced by the reference itself."""
+    g = np.load(os.path.join(golden_dir, "cluster_views.npz"))
+    imgs = []
+    for i in range(int(g["n"])):
+        img = R.generate_cluster_visualization(g[f"pts_{i}"])
+        assert np.array_equal(img, g[f"img_{i}"]), i
+        imgs.append(img)
+    assert np.array_equal(R.cluster_mosaic(imgs[:5]), g["mosaic"])
