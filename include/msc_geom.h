@@ -189,6 +189,15 @@ int msc_cluster_views(const float* pts_xyzi, const uint32_t* order, const int32_
                       int32_t max_cluster_points, const float* center_scale, uint32_t* keys, uint32_t* irange, uint8_t* out_bgr,
                       void* stream);
 
+/* DBSCAN with scikit-learn's labelling (reference call site LiDARAgent._detect_objects_3d, lidar_agent.py:148-153):
+ * float64 neighbour relation, clusters numbered by their smallest core index, border points take the smallest adjacent
+ * cluster number, noise = -1.  pts: rows of `pitch` floats (xyz first).  origin / cell / dims describe a host-chosen grid
+ * of cubic cells (cell >= eps) covering the points.  labels: device i32[n]; n_clusters_host: host int.  SYNCHRONOUS on
+ * `stream`.  workspace >= msc_dbscan_workspace_bytes(n, dims). */
+size_t msc_dbscan_workspace_bytes(uint32_t n, const int32_t dims[3]);
+int msc_dbscan(const float* pts, uint32_t n, int32_t pitch, double eps, int32_t min_samples, const double origin[3], double cell,
+               const int32_t dims[3], int32_t* labels, int32_t* n_clusters_host, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,8 +5,8 @@ Same constructor, attribute names, method names, argument meaning and return sha
 (SURVEY.md section 8(b)), so the three geometry methods the reference's scripts call directly
 (src/export_sample_data.py:59-65, src/generate_detailed_logs.py:213-215) and `process()` are drop-ins.
 What stays on the host, and why:
-  * DBSCAN (lidar_agent.py:148-151): border-point assignment is visit-order dependent; label parity on a GPU is a
-    research problem.  Cluster list order follows CPython set iteration like the reference.
+  * the cluster LIST ORDER follows CPython set iteration over the labels, like the reference (lidar_agent.py:154-159);
+    DBSCAN itself runs on the device with scikit-learn's exact labelling (csrc/dbscan.cu).
   * the cv2 overlays drawn after the raster (lidar_agent.py:599-634) and the log1p density normalisation, which is
     evaluated with NumPy's own float32 log1p through a count -> value table so the uint8 layer is bit-identical.
   * every remote LLM call: injected as callables (`llm`, `cluster_classifier`); absent callables yield the
@@ -117,6 +117,7 @@ class LiDARAgent:
         self.bev_resolution = 800      # :48
         self.bev_range = 50            # :49
         self.engine = engine or GeometryEngine()
+        self.dbscan_backend = "cuda"  # "sklearn" restores the reference's CPU call; labels are identical either way
         self.llm = llm
         self.cluster_classifier = cluster_classifier
 
@@ -168,8 +169,11 @@ class LiDARAgent:
     def _detect_objects_3d(self, object_points: np.ndarray) -> List[DetectedObject]:
         if len(object_points) < self.dbscan_min_samples:
             return []
-        from sklearn.cluster import DBSCAN
-        labels = DBSCAN(eps=self.dbscan_eps, min_samples=self.dbscan_min_samples).fit(object_points[:, :3]).labels_
+        if self.dbscan_backend == "sklearn":
+            from sklearn.cluster import DBSCAN
+            labels = DBSCAN(eps=self.dbscan_eps, min_samples=self.dbscan_min_samples).fit(object_points[:, :3]).labels_
+        else:
+            labels = ops.dbscan(self.engine, object_points, self.dbscan_eps, self.dbscan_min_samples)
         uniq = set(labels)
         uniq.discard(-1)
         order = [int(l) for l in uniq if int((labels == l).sum()) >= 5]  # set-iteration order, like lidar_agent.py:154-165

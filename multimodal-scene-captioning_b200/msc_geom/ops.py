@@ -233,3 +233,32 @@ def cluster_views(eng: GeometryEngine, points: np.ndarray, clusters) -> np.ndarr
                                           irange.data_ptr(), out.data_ptr(), _stream(eng)), "msc_cluster_views")
     eng.kernel_launches += 2
     return out.cpu().numpy()
+
+
+def dbscan(eng: GeometryEngine, xyz: np.ndarray, eps: float = 0.5, min_samples: int = 10) -> np.ndarray:
+    """sklearn.cluster.DBSCAN(eps, min_samples).fit(xyz).labels_ (lidar_agent.py:148-153), computed on the device with
+    scikit-learn's own labelling rule (see csrc/dbscan.cu).  Returns int64 labels like scikit-learn."""
+    rows, pitch = _raw_rows(xyz)
+    n = int(rows.shape[0])
+    if n == 0:
+        return np.zeros(0, np.int64)
+    lo = rows[:, :3].min(axis=0).astype(np.float64)
+    hi = rows[:, :3].max(axis=0).astype(np.float64)
+    cell = float(eps) * (1.0 + 1e-6)  # a hair above eps so float rounding can never put neighbours two cells apart
+    while True:
+        dims = np.maximum(np.floor((hi - lo) / cell).astype(np.int64) + 1, 1)
+        if int(dims.prod()) <= (1 << 24):
+            break
+        cell *= 2.0  # coarser cells stay correct (cell >= eps), only slower
+    d = eng.device
+    src = torch.from_numpy(np.ascontiguousarray(rows)).to(d)
+    labels = torch.empty(n, dtype=torch.int32, device=d)
+    c_dims = (C.c_int32 * 3)(*[int(v) for v in dims])
+    c_org = (C.c_double * 3)(*[float(v) for v in lo])
+    need = int(eng.lib.msc_dbscan_workspace_bytes(n, c_dims))
+    ws = torch.empty(need, dtype=torch.uint8, device=d)
+    k = C.c_int32(0)
+    _capi.check(eng.lib.msc_dbscan(src.data_ptr(), n, pitch, C.c_double(float(eps)), int(min_samples), c_org, C.c_double(cell), c_dims,
+                                   labels.data_ptr(), C.byref(k), ws.data_ptr(), need, _stream(eng)), "msc_dbscan")
+    eng.kernel_launches += 8
+    return labels.cpu().numpy().astype(np.int64)

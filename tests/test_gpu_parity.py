@@ -238,6 +238,41 @@ def test_cluster_metadata_matches_reference(engine, golden_dir):
         assert m["distance"] == g["distance"][i] and m["num_points"] == g["num_points"][i] and m["direction"] == str(g["direction"][i])
 
 
+def _dbscan_cases():
+    rng = np.random.default_rng(4)
+    blobs = np.concatenate([rng.normal(c, s, (m, 3)) for c, s, m in [((0, 0, 0), 0.3, 400), ((2.2, 0, 0), 0.35, 300), ((10, 5, 1), 0.15, 60),
+                                                                      ((-6, -6, 0), 1.5, 800), ((4, -9, 0.5), 0.05, 12)]]).astype(np.float32)
+    lattice = np.stack(np.meshgrid(np.arange(12) * 0.5, np.arange(12) * 0.5, np.arange(3) * 0.5), -1).reshape(-1, 3).astype(np.float32)  # distances exactly eps
+    dup = np.repeat(rng.uniform(-3, 3, (40, 3)).astype(np.float32), 11, 0)                                                              # exact duplicates
+    sparse = rng.uniform(-40, 40, (3000, 3)).astype(np.float32)                                                                        # all noise
+    return {"blobs": blobs, "lattice": lattice, "duplicates": dup, "noise": sparse, "tiny": blobs[:7]}
+
+
+@pytest.mark.parametrize("case", ["blobs", "lattice", "duplicates", "noise", "tiny", "synth_k1", "synth_k10"])
+def test_dbscan_labels_equal_sklearn(engine, case):
+    """device DBSCAN must reproduce sklearn.cluster.DBSCAN(eps=0.5, min_samples=10) label for label
+    (the reference's call, lidar_agent.py:148-153), on the [EXT]-aggregated object points too."""
+    from sklearn.cluster import DBSCAN
+    if case.startswith("synth"):
+        s = make_sample(7, n_sweeps=1 if case.endswith("k1") else 10)
+        xyzi, _ = ops.aggregate_sweeps(engine, [(sw["points_raw"], sw["ref_from_sensor"], sw["time_lag"]) for sw in s["lidar_sweeps"]])
+        _, _, obj = ops.keyframe_filter_split(engine, xyzi, GeomParams(bev_res=800))
+        X = obj[:, :3]
+        if case.endswith("k10"):
+            X = X[np.abs(X[:, 0]) < 25]          # keep the CPU side of the comparison to a few seconds
+    else:
+        X = _dbscan_cases()[case]
+    ref = DBSCAN(eps=0.5, min_samples=10).fit(X).labels_
+    got = ops.dbscan(engine, X, 0.5, 10)
+    assert got.dtype == ref.dtype and np.array_equal(got, ref), (case, int((got != ref).sum()), int(ref.max()) + 1)
+    if case == "blobs":
+        assert ref.max() >= 2 and (ref == -1).any()
+        ref2 = DBSCAN(eps=0.3, min_samples=4).fit(X).labels_
+        assert np.array_equal(ops.dbscan(engine, X, 0.3, 4), ref2)
+        pc4 = np.concatenate([X, np.ones((len(X), 1), np.float32)], 1)   # (N,4) rows, like object_points[:, :3] of an (N,4) cloud
+        assert np.array_equal(ops.dbscan(engine, pc4[:, :3], 0.5, 10), ref)
+
+
 def test_cluster_views_match_reference(engine, golden_dir):
     """Cluster 4-view raster (lidar_agent.py:241-356) and mosaic (:366-386): exact uint8 equality with the reference's images."""
     from msc_geom.lidar_agent import LiDARAgent, cluster_mosaic
