@@ -1,0 +1,40 @@
+"""Timing of the SURVEY 8(f) rows (GPU DBSCAN, cluster 4-view raster) and of the keyframe drop-in methods against their CPU
+counterparts (scikit-learn / the NumPy restatement of the reference) on one synthetic sample.  Prints one JSON line."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-scene-captioning_b200")); sys.path.insert(0, ROOT)
+import numpy as np, torch
+from sklearn.cluster import DBSCAN
+from msc_geom import ops
+from msc_geom.engine import GeometryEngine
+from msc_geom.layout import GeomParams
+from msc_geom.lidar_agent import LiDARAgent
+from msc_geom.synthetic import make_sample
+from oracle import numpy_ref as R
+
+def timeit(f, reps):
+    f(); torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(reps): f()
+    torch.cuda.synchronize(); return (time.perf_counter() - t) / reps
+
+eng = GeometryEngine(); agent = LiDARAgent(object(), "m", "n", engine=eng)
+out = {}
+for name, nsw in (("K1", 1), ("K10", 10)):
+    s = make_sample(3, n_sweeps=nsw)
+    sweeps = [(sw["points_raw"], sw["ref_from_sensor"], sw["time_lag"]) for sw in s["lidar_sweeps"]]
+    xyzi, _ = ops.aggregate_sweeps(eng, sweeps)
+    kept, ground, obj = ops.keyframe_filter_split(eng, xyzi, GeomParams(bev_res=800))
+    r = {"points": int(len(xyzi)), "object_points": int(len(obj))}
+    r["filter_split_gpu_ms"] = 1e3 * timeit(lambda: ops.keyframe_filter_split(eng, xyzi, GeomParams(bev_res=800)), 5)
+    t = time.perf_counter(); k2 = R.preprocess_point_cloud(xyzi); g2, o2 = R.segment_ground(k2); r["filter_split_numpy_ms"] = 1e3 * (time.perf_counter() - t)
+    r["bev_gpu_ms"] = 1e3 * timeit(lambda: agent._generate_multi_layer_bev(ground, obj), 3)
+    t = time.perf_counter(); R.generate_multi_layer_bev(ground, obj); r["bev_numpy_restatement_ms"] = 1e3 * (time.perf_counter() - t)
+    r["dbscan_gpu_ms"] = 1e3 * timeit(lambda: ops.dbscan(eng, obj[:, :3], 0.5, 10), 3)
+    t = time.perf_counter(); lab = DBSCAN(eps=0.5, min_samples=10).fit(obj[:, :3]).labels_; r["dbscan_sklearn_ms"] = 1e3 * (time.perf_counter() - t)
+    order = [int(l) for l in set(lab) if l != -1 and (lab == l).sum() >= 5][:10]
+    if order:
+        r["clusters_rastered"] = len(order)
+        r["cluster_views_gpu_ms"] = 1e3 * timeit(lambda: agent._cluster_visualizations(obj, lab, order), 3)
+        t = time.perf_counter(); [R.generate_cluster_visualization(obj[lab == l]) for l in order]; r["cluster_views_numpy_restatement_ms"] = 1e3 * (time.perf_counter() - t)
+    out[name] = r
+print(json.dumps(out))
