@@ -26,8 +26,12 @@
 namespace msc {
 
 // Launch shape: NT threads = NT/32 warps; every warp owns a private ring of STAGES tiles of 32*PPT points.
-template <int NT, int PPT, int STAGES, bool POSE_SMEM = false>
+template <int NT, int PPT, int STAGES, bool POSE_SMEM = false, int QUEUE = 0>
 struct Cfg {
+    // QUEUE = 1: per-warp queue of points that have candidate boxes, drained 32 at a time so every lane tests a real candidate
+    // (deferring the exact wedge tests of straddling cells the same way was measured slower and is not implemented)
+    static constexpr int kQueue = QUEUE;
+    static constexpr int kQueueBytes = QUEUE ? (NT / 32) * 64 * 16 : 0;
     static constexpr bool kPoseInSmem = POSE_SMEM;  // pose rows read from smem per tile (64-register budgets)
     static constexpr int kThreads = NT;
     static constexpr int kWarps = NT / 32;
@@ -49,7 +53,7 @@ constexpr int kAccWords = 9;                  // per-box accumulators: count, mi
 constexpr int kMaxWarps = 32;
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
-    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, lut_off, misc_off, total_bytes;
+    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, lut_off, misc_off, queue_off, total_bytes;
     int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
     int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
     int32_t max_boxes;             // capacity of the smem box tables
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
     const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* const ring = reinterpret_cast<float*>(smem + L.tiles_off) + (size_t)warp * S * (C::kTileBytes / 4);  // this warp's slots
     uint64_t* const full = misc->full_bar + warp * 8;
+    float4* const queue = reinterpret_cast<float4*>(smem + L.queue_off) + warp * 64;  // this warp's ring of pending candidate points
     const int res = P.bev_res, res_m1 = P.bev_res - 1;
     const size_t ncell = (size_t)res * (size_t)res;
     const int n_cams = P.n_cams;
@@ -444,6 +449,29 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
         uint32_t c_close = 0, c_kept = 0, c_ground = 0;  // per-thread counters (flushed once per sample)
         uint32_t cam_lo = 0, cam_hi = 0;                 // eight 8-bit per-camera counters, spilled every <= 255 points
         uint32_t cam_pts = 0;
+        uint32_t q_head = 0, q_cnt = 0;  // warp-uniform: every lane derives them from the same ballots
+        // test the queued point of this lane against its candidate boxes; accumulate the (usually single) containing box once
+        // test the queued point of this lane against its candidate boxes; accumulate the (usually single) containing box once
+        auto drain_queue = [&](uint32_t n_take) {
+            const bool act = (uint32_t)lane < n_take;
+            const float4 e = queue[(q_head + lane) & 63u];
+            __syncwarp();  // every lane has read its slot before any lane can enqueue over it again
+            if (act) {
+                uint32_t ids = __float_as_uint(e.w);
+                const float es2 = __fadd_rn(__fmul_rn(e.x, e.x), __fmul_rn(e.y, e.y));
+                int hit = -1;
+                do {
+                    const int b = (int)(ids & 0xffu);
+                    if (box_contains(boxp, b, e.x, e.y, e.z)) {
+                        if (hit >= 0) box_accumulate(A, boxacc, b, e.x, e.y, e.z, es2); else hit = b;
+                    }
+                    ids = (ids >> 8) | 0xff000000u;
+                } while ((ids & 0xffu) != 0xffu);
+                if (hit >= 0 && !(A.debug_skip & 8u)) box_accumulate(A, boxacc, hit, e.x, e.y, e.z, es2);
+            }
+            q_head = (q_head + n_take) & 63u;
+            q_cnt -= n_take;
+        };
         double M[MSMEM ? 1 : 12];
         const double* Ms = nullptr;
         for (;;) {
@@ -510,8 +538,10 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
                 ce[u] = cull[(iy[u] >> L.cull_shift) * L.cull_dim + (ix[u] >> L.cull_shift)];
             }
             // ---- phase B: data-dependent work per kept point
+            uint32_t cand[PPT];
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
+                cand[u] = kCullEmpty;
                 if (!keep[u]) continue;
                 if (FOV) {
                     uint32_t in_bits = ce[u].y & 0xffu;
@@ -543,6 +573,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
                     atomicAdd(reinterpret_cast<unsigned long long*>(g_ci) + cell, 1ull | ((unsigned long long)q << 32));
                 }
                 if (zr[u] > 0.0f && !(A.debug_skip & 1u)) atomicMax(reinterpret_cast<int*>(g_h) + cell, __float_as_int(zr[u]));  // :560, 0-initialised max
+                if (C::kQueue) { cand[u] = (A.debug_skip & 2u) ? kCullEmpty : ce[u].x; continue; }  // enqueued after the loop
                 // A.2 oriented-box membership for the candidate boxes of this cull cell
                 uint32_t ids = ce[u].x;
                 if (ids == kCullEmpty || (A.debug_skip & 2u)) continue;
@@ -565,6 +596,31 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
                 }
                 if (hit >= 0 && !(A.debug_skip & 8u)) box_accumulate(A, boxacc, hit, xr[u], yr[u], zr[u], s2[u]);
             }
+            if (C::kQueue) {
+                // ---- phase C: points that have candidate boxes go to this warp's queue; whenever 32 are pending every lane tests
+                // one of them (dense), instead of a handful of lanes looping while the rest of the warp idles
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    if (cand[u] == kCullAll) {  // crowded cell (more than four boxes): rare, test every box in place
+                        int hit = -1;
+                        for (int b = 0; b < n_boxes; ++b)
+                            if (box_contains(boxp, b, xr[u], yr[u], zr[u])) {
+                                if (hit >= 0) box_accumulate(A, boxacc, b, xr[u], yr[u], zr[u], s2[u]); else hit = b;
+                            }
+                        if (hit >= 0 && !(A.debug_skip & 8u)) box_accumulate(A, boxacc, hit, xr[u], yr[u], zr[u], s2[u]);
+                        cand[u] = kCullEmpty;
+                    }
+                    const bool has = cand[u] != kCullEmpty;
+                    const uint32_t m = __ballot_sync(0xffffffffu, has);
+                    if (m == 0u) continue;
+                    const uint32_t add = __popc(m);
+                    if (q_cnt + add > 64u) drain_queue(32u);
+                    if (has) queue[(q_head + q_cnt + __popc(m & ((1u << lane) - 1u))) & 63u] = make_float4(xr[u], yr[u], zr[u], __uint_as_float(cand[u]));
+                    q_cnt += add;
+                    __syncwarp();
+                    if (q_cnt >= 32u) drain_queue(32u);
+                }
+            }
             ++wk;
             c_first += W * TP;
             if (FOV) {
@@ -578,6 +634,10 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
                     cam_lo = cam_hi = cam_pts = 0;
                 }
             }
+        }
+
+        if (C::kQueue) {
+            while (q_cnt > 0u) drain_queue(min(q_cnt, 32u));
         }
 
         // ------------------------------------------------------------ epilogue
@@ -650,7 +710,8 @@ static int g_opt_window = 0;       // 0 = auto (largest that fits)
 static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
 static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
 static int g_opt_debug_skip = 0;
-static int g_opt_config = 2;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem
+static int g_opt_config = 6;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem;
+                              // 3 = 512x4,2; 4 = 768x2,3; 5 = 1024x1,4; 6 = shape 2 + per-warp candidate queue (default)
 static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 
 // divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
@@ -685,12 +746,13 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes)
     return T;
 }
 
-static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, FusedLayout* L) {
+static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, int queue_bytes, FusedLayout* L) {
     const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
     cull_geometry(P, &L->cull_shift, &L->cull_dim);
     L->max_boxes = cap;
     int off = 0;
     L->tiles_off = off; off += ring_bytes; off = (off + 127) & ~127;
+    L->queue_off = off; off += queue_bytes; off = (off + 127) & ~127;
     L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
@@ -721,7 +783,7 @@ static int launch_fused(const FusedArgs& args, const TableLayout& T, unsigned ch
 template <class C>
 static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid, bool fov,
                           bool fast, cudaStream_t stream) {
-    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, &args.L) != 0) {
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, C::kQueueBytes, &args.L) != 0) {
         set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
         return MSC_ERR_UNSUPPORTED;
     }
@@ -829,6 +891,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
         case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 3: return dispatch_fused<Cfg<512, 4, 2>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 6: return dispatch_fused<Cfg<1024, 2, 2, true, 1>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 4: return dispatch_fused<Cfg<768, 2, 3, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 5: return dispatch_fused<Cfg<1024, 1, 4, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         default: return dispatch_fused<Cfg<512, 2, 4>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);

@@ -18,7 +18,7 @@ from tests import oracle_bridge as OB
 IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
 
 
-def check_fused(eng, samples, params=None, config=2, n_cams=6):
+def check_fused(eng, samples, params=None, config=6, n_cams=6):
     p = params or GeomParams()
     _capi.set_option("config", config)
     hb = pack_batch(samples, n_cams=n_cams)
@@ -40,7 +40,7 @@ def check_fused(eng, samples, params=None, config=2, n_cams=6):
     return hb, got
 
 
-@pytest.mark.parametrize("config", [0, 1, 2])
+@pytest.mark.parametrize("config", [0, 2, 3, 6])
 def test_fused_config3_shape(engine, config):
     check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
 
@@ -60,7 +60,7 @@ def test_fused_ragged_and_empty_inputs(engine):
     c = make_sample(32, n_sweeps=1, n_boxes=3)
     c["lidar_sweeps"] = [dict(c["lidar_sweeps"][0], points_raw=c["lidar_sweeps"][0]["points_raw"][:0])]  # no points at all
     d = {"point_cloud": np.random.default_rng(5).normal(0, 12, (5000, 4)).astype(np.float32), "annotations": []}  # plain reference-style sample
-    for cfg in (1, 2):
+    for cfg in (1, 2, 6):
         check_fused(engine, [a, b, c, d], config=cfg)
 
 
@@ -142,7 +142,7 @@ def test_fused_full_size_batch_properties(engine):
     equality (bit-reproducibility under different scheduling), idempotence, and the oracle on sampled samples."""
     import torch
     p = GeomParams()
-    _capi.set_option("config", 2)
+    _capi.set_option("config", 6)
     uniq = [make_sample(100 + i, n_sweeps=10, n_boxes=60) for i in range(8)]
     hb_u = pack_batch(uniq)
     hb = tile_batch(hb_u, 74)

@@ -7,7 +7,7 @@ from msc_geom.engine import GeometryEngine
 from msc_geom import _capi
 eng = GeometryEngine()
 import os
-_capi.set_option('config', int(os.environ.get('MSC_CONFIG','2')))
+_capi.set_option('config', int(os.environ.get('MSC_CONFIG','6')))
 print('device', torch.cuda.get_device_name(), 'sms', eng.sm_count, 'smem', eng.smem_optin)
 samples = [make_sample(i, n_sweeps=10 if i%2==0 else 3, n_boxes='mini' if i%3==0 else 60) for i in range(5)]
 hb = pack_batch(samples)
