@@ -306,7 +306,8 @@ def main():
     if not args.no_cpu and world == 1:
         n_cpu = args.cpu_samples or 4 * cores
         v, dt = cpu_oracle_throughput(hb_u, params, n_cpu, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v1, _ = cpu_oracle_throughput(hb_u, params, 4, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": v1,
                "sample": f"{n_cpu} samples of the same workload, scalar C oracle (oracle/c/msc_oracle.c), {cores} threads, {dt:.1f} s wall"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
