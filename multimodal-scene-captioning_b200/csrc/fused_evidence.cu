@@ -53,7 +53,7 @@ constexpr int kAccWords = 9;                  // per-box accumulators: count, mi
 constexpr int kMaxWarps = 32;
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
-    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, lut_off, misc_off, queue_off, total_bytes;
+    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, misc_off, queue_off, total_bytes;
     int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
     int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
     int32_t max_boxes;             // capacity of the smem box tables
@@ -80,24 +80,12 @@ struct Misc {  // small per-CTA state at misc_off
     double pose[kMaxSweepsSmem * 12];  // this sample's 3x4 sweep transforms (only used by POSE_SMEM shapes)
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int R>
-__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R>
-__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 // volatile so the compiler can neither rematerialise nor re-issue the load: the pose stays in registers
 __device__ __forceinline__ void ld_pose(const double* __restrict__ p, double M[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i += 2)
         asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(M[i]), "=d"(M[i + 1]) : "l"(p + i));
 }
-template <int N>
-__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the NT consumer threads only
-    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
-}
-
 // BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
 // sequence, which tools/markstein_check.c proves equal to RN(a/b) for every float a outside the subnormal
 // quotient range for the whitelisted divisors (a = fl(c + r) is 0 or >= 2^-24 r here).
@@ -756,7 +744,6 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
     L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
-    L->lut_off = 0;
     L->misc_off = off; off += (int)((sizeof(Misc) + 127) & ~127);
     L->window_off = off;
     const int avail = smem_limit - off;

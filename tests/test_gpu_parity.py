@@ -118,6 +118,28 @@ def test_fused_other_grid_and_exact_division_path(engine):
     assert _capi.get_option("last_fastdiv") == 1
 
 
+def test_fused_many_sweeps_and_camera_counts(engine):
+    """More sweeps than the kernel caches in shared memory (64): the sweep table and poses fall back to global memory.
+    Also 0 and 8 cameras."""
+    from msc_geom.geometry import ref_from_sweep
+    base = make_sample(95, n_sweeps=10, n_boxes=12)
+    sw = []
+    for k in range(70):
+        src = base["lidar_sweeps"][k % 10]
+        M = src["ref_from_sensor"].copy()
+        M[:, 3] += 0.01 * k                         # every sweep gets its own transform
+        sw.append(dict(src, points_raw=src["points_raw"][k * 97: k * 97 + 700 + 13 * k], ref_from_sensor=M))
+    many = dict(base, lidar_sweeps=sw)
+    for cfg in (0, 6):
+        check_fused(engine, [many, make_sample(96, n_sweeps=2, n_boxes=5)], config=cfg)
+    s0 = make_sample(97, n_sweeps=2, n_boxes=9)
+    s0["cameras"] = []
+    check_fused(engine, [s0], params=GeomParams(n_cams=0), n_cams=0)
+    s8 = make_sample(98, n_sweeps=2, n_boxes=9)
+    s8["cameras"] = s8["cameras"] + [dict(s8["cameras"][1], channel="CAM_X1"), dict(s8["cameras"][4], channel="CAM_X2")]
+    check_fused(engine, [s8], params=GeomParams(n_cams=8), n_cams=8)
+
+
 def test_fused_fov_counts_off_and_small_window(engine):
     s = [make_sample(70, n_sweeps=2, n_boxes=20)]
     _capi.set_option("fov", 0)
