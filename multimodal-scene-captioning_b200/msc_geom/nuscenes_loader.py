@@ -43,6 +43,9 @@ class MockNuScenesLoader:
                 "images": images, "camera_names": self.camera_channels, "point_cloud": point_cloud, "annotations": [car, adult],
                 "metadata": {"location": "boston-seaport", "nbr_objects": 2}}
 
+    def scene_sample_tokens(self, scene_token: str) -> List[str]:
+        return [f"mock_sample_{i:03d}" for i in range(5)]
+
     def load_scene_samples(self, scene_token: str, max_samples: Optional[int] = None) -> List[Dict]:
         return [self.load_sample(f"mock_sample_{i:03d}") for i in range(min(max_samples or 5, 5))]
 
@@ -63,6 +66,10 @@ class SyntheticNuScenesLoader:
 
     def load_sample(self, sample_token: str) -> Dict:
         return make_sample(int(sample_token.rsplit("_", 1)[1]), n_sweeps=self.n_sweeps, n_boxes=self.n_boxes, with_images=self.with_images)
+
+    def scene_sample_tokens(self, scene_token: str) -> List[str]:
+        s = int(scene_token.rsplit("_", 1)[1])
+        return [f"synth_sample_{s * self.samples_per_scene + i:06d}" for i in range(self.samples_per_scene)]
 
     def load_scene_samples(self, scene_token: str, max_samples: Optional[int] = None) -> List[Dict]:
         s = int(scene_token.rsplit("_", 1)[1])
@@ -129,6 +136,15 @@ class NuScenesLoader:
                 "images": images, "camera_names": names, "point_cloud": sweeps[0]["points_raw"][:, :4], "annotations": annotations,
                 "metadata": {"location": nusc.get("log", scene["log_token"])["location"], "nbr_objects": len(annotations)},
                 "lidar_sweeps": sweeps, "ego_pose": ref_pose, "lidar_calib": ref_cal, "cameras": cameras}
+
+    def scene_sample_tokens(self, scene_token: str) -> List[str]:
+        """Tokens of a scene's samples from the table links alone (the reference's evaluator loads every image and point cloud
+        just to learn these, src/evaluation_framework.py:488-496)."""
+        tok, out = self.nusc.get("scene", scene_token)["first_sample_token"], []
+        while tok != "":
+            out.append(tok)
+            tok = self.nusc.get("sample", tok)["next"]
+        return out
 
     def load_scene_samples(self, scene_token: str, max_samples: Optional[int] = None) -> List[Dict]:
         tok, out = self.nusc.get("scene", scene_token)["first_sample_token"], []

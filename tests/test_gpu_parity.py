@@ -406,6 +406,26 @@ def test_patch_reference_style_classes(engine, golden_dir):
     assert [o["id"] for o in sg._build_spatial_zones(objs)["right_medium"]] == ["obj_0"]
 
 
+def test_staged_files_batch_runs_from_pinned_memory(engine, tmp_path):
+    """sweeps read from .pcd.bin files straight into a pinned batch buffer give the same evidence."""
+    import torch
+    from msc_geom import io as mio
+    samples = [make_sample(110 + i, n_sweeps=2, n_boxes=6) for i in range(2)]
+    fsamples = []
+    for i, s in enumerate(samples):
+        fs = dict(s); fs["lidar_sweeps"] = []
+        for k, sw in enumerate(s["lidar_sweeps"]):
+            path = str(tmp_path / f"s{i}_{k}.pcd.bin"); mio.write_pcd_bin(path, sw["points_raw"])
+            fs["lidar_sweeps"].append({"path": path, "ref_from_sensor": sw["ref_from_sensor"], "time_lag": sw["time_lag"]})
+        fsamples.append(fs)
+    hb = mio.stage_batch(fsamples, threads=4)
+    assert hb._pinned_holder is not None and hb._pinned_holder.is_pinned()
+    a = engine.run_fused(engine.upload(hb, non_blocking=True)); torch.cuda.synchronize(); a = a.to_host()
+    b = engine.run_fused(engine.upload(pack_batch(samples))); torch.cuda.synchronize(); b = b.to_host()
+    for k in ("box_count", "box_centroid", "bev_count", "bev_isum_q", "bev_height", "stats", "proj_extent"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_bad_arguments_raise(engine):
     from msc_geom.engine import make_params
     s = make_sample(90, n_sweeps=1, n_boxes=4)

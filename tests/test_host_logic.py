@@ -104,3 +104,39 @@ def test_shard_range_partitions(n, world):
     assert spans[0][0] == 0 and spans[-1][1] == n
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert max(hi - lo for lo, hi in spans) == (n + world - 1) // world if n else True
+
+
+def test_stage_batch_from_files_equals_pack_batch(tmp_path):
+    """.pcd.bin sweeps read in place into the batch layout give exactly what pack_batch builds in memory."""
+    from msc_geom import io as mio
+    samples = [make_sample(i, n_sweeps=3, n_boxes=4 + i) for i in range(3)]
+    samples[2]["lidar_sweeps"][1]["points_raw"] = samples[2]["lidar_sweeps"][1]["points_raw"][:1001]
+    file_samples = []
+    for i, s in enumerate(samples):
+        fs = dict(s)
+        fs["lidar_sweeps"] = []
+        for k, sw in enumerate(s["lidar_sweeps"]):
+            path = str(tmp_path / f"s{i}_{k}.pcd.bin")
+            mio.write_pcd_bin(path, sw["points_raw"])
+            assert mio.pcd_bin_points(path) == sw["points_raw"].shape[0]
+            fs["lidar_sweeps"].append({"path": path, "ref_from_sensor": sw["ref_from_sensor"], "time_lag": sw["time_lag"]})
+        file_samples.append(fs)
+    file_samples[1]["lidar_sweeps"][0] = samples[1]["lidar_sweeps"][0]          # in-memory sweeps can be mixed in
+    a, b = pack_batch(samples), mio.stage_batch(file_samples, threads=4, pinned=False)
+    for k in ("sample_sweep_off", "sweep_start", "sweep_count", "sweep_pose", "sweep_time_lag", "sample_box_off", "boxes", "ego_pose", "lidar_calib",
+              "cam_ego_pose", "cam_calib", "cam_K"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.points, b.points, equal_nan=True) and b.max_boxes_per_sample == a.max_boxes_per_sample
+    with open(tmp_path / "bad.pcd.bin", "wb") as f:
+        f.write(b"\0" * 30)
+    with pytest.raises(ValueError):
+        mio.pcd_bin_points(str(tmp_path / "bad.pcd.bin"))
+
+
+def test_token_only_scene_scan():
+    from msc_geom.nuscenes_loader import SyntheticNuScenesLoader, create_loader
+    ld = SyntheticNuScenesLoader(n_scenes=3, samples_per_scene=4, n_sweeps=1)
+    toks = [t for sc in ld.get_scene_list() for t in ld.scene_sample_tokens(sc["token"])]
+    assert len(toks) == 12 and toks[5] == "synth_sample_000005"
+    assert ld.load_sample(toks[5])["sample_token"] == toks[5]
+    assert len(create_loader(None, use_mock=True).scene_sample_tokens("mock_scene_001")) == 5

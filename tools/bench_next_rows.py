@@ -37,4 +37,30 @@ for name, nsw in (("K1", 1), ("K10", 10)):
         r["cluster_views_gpu_ms"] = 1e3 * timeit(lambda: agent._cluster_visualizations(obj, lab, order), 3)
         t = time.perf_counter(); [R.generate_cluster_visualization(obj[lab == l]) for l in order]; r["cluster_views_numpy_restatement_ms"] = 1e3 * (time.perf_counter() - t)
     out[name] = r
+# on-disk step: 40 sweeps (one 4-sample batch of 10 sweeps) from files in the page cache
+import tempfile
+from msc_geom import io as mio
+from msc_geom.layout import pack_batch
+with tempfile.TemporaryDirectory() as d:
+    samples = [make_sample(200 + i, n_sweeps=10) for i in range(4)]
+    fs = []
+    for i, s in enumerate(samples):
+        f = dict(s); f["lidar_sweeps"] = []
+        for k, sw in enumerate(s["lidar_sweeps"]):
+            path = os.path.join(d, f"{i}_{k}.pcd.bin"); mio.write_pcd_bin(path, sw["points_raw"])
+            f["lidar_sweeps"].append({"path": path, "ref_from_sensor": sw["ref_from_sensor"], "time_lag": sw["time_lag"]})
+        fs.append(f)
+    mio.stage_batch(fs, threads=8)
+    t = time.perf_counter(); hb = mio.stage_batch(fs, threads=8); t_stage = time.perf_counter() - t
+    def devkit_style():
+        ss = []
+        for f in fs:
+            g = dict(f); g["lidar_sweeps"] = [dict(sw, points_raw=np.fromfile(sw["path"], dtype=np.float32).reshape(-1, 5)) for sw in f["lidar_sweeps"]]
+            ss.append(g)
+        return pack_batch(ss)
+    devkit_style()
+    t = time.perf_counter(); devkit_style(); t_ref = time.perf_counter() - t
+    mb = hb.points.nbytes / 1e6
+    out["io_4x10_sweeps"] = {"megabytes": mb, "stage_in_place_pinned_ms": 1e3 * t_stage, "fromfile_then_pack_ms": 1e3 * t_ref,
+                             "stage_GBps": mb / 1e3 / t_stage}
 print(json.dumps(out))
