@@ -36,8 +36,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples-per-gpu", type=int, default=592, help="batch per rank (4 per SM); inputs ~4.1 GB >> L2")
     ap.add_argument("--unique", type=int, default=37, help="distinct synthetic samples generated per rank, tiled to the batch")
-    ap.add_argument("--workload", default="config3", choices=["config3", "config2", "mini"],
-                    help="config3: 10 sweeps, 60 boxes; config2: single keyframe; mini: 10 sweeps, 60-120 boxes")
+    ap.add_argument("--workload", default="config3", choices=["config3", "config2", "mini", "mini404", "trainval"],
+                    help="config3: 10 sweeps, 60 boxes (weak scaling, the metric's config); config2: single keyframes; mini: 10 sweeps, 60-120 "
+                         "boxes; mini404: BASELINE config 4, 404 samples sharded over the ranks (strong scaling); trainval: BASELINE config 5, "
+                         "34,149 samples sharded over the ranks + a 200-annotation relation table per sample (needs 8 GPUs)")
+    ap.add_argument("--total-samples", type=int, default=0, help="override the total of the strong-scaling workloads (testing)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -55,6 +58,10 @@ def workload_kwargs(name):
         return dict(n_sweeps=1, n_boxes=60), "config2: 1 keyframe x 34,720 pts, 60 boxes, 6 cams, BEV 200x200"
     if name == "mini":
         return dict(n_sweeps=10, n_boxes="mini"), "config4-shape: 10 sweeps x 34,720 pts, 60-120 boxes, 6 cams, BEV 200x200"
+    if name == "mini404":
+        return dict(n_sweeps=10, n_boxes="mini"), "config4: 404 samples x 10 sweeps x 34,720 pts, 60-120 boxes, sharded over the ranks"
+    if name == "trainval":
+        return dict(n_sweeps=10, n_boxes=60), "config5: 34,149 samples x 10 sweeps x 34,720 pts, 60 boxes + 200-annotation relation table, sharded"
     return dict(n_sweeps=10, n_boxes=60), "config3: 10 sweeps x 34,720 pts (347,200), 60 boxes, 6 cams, BEV 200x200 @0.5m"
 
 
@@ -134,7 +141,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    from msc_geom.layout import GeomParams, pack_batch, tile_batch
+    from msc_geom.dist import shard_range
+    from msc_geom.layout import GeomParams, pack_batch, tile_batch, truncate_batch
     from msc_geom.synthetic import make_sample
 
     params = GeomParams()
@@ -182,14 +190,26 @@ def main():
     _capi.set_option("cull_shift", args.cull_shift)
     _capi.set_option("debug_skip", args.debug_skip)
 
-    S = args.samples_per_gpu
+    strong_total = {"mini404": 404, "trainval": 34149}.get(args.workload, 0)
+    if strong_total:
+        strong_total = args.total_samples or strong_total
+        lo, hi = shard_range(strong_total, rank, world)
+        S = hi - lo
+    else:
+        S = args.samples_per_gpu
     n_unique = max(1, min(args.unique, S))
     reps = (S + n_unique - 1) // n_unique
     base = rank * 100000
     hb_u = pack_batch([make_sample(base + i, **wkw) for i in range(n_unique)])
-    hb = tile_batch(hb_u, reps)
+    db = eng.upload_tiled(hb_u, reps, S if strong_total else None)  # one host copy of the distinct samples, replicated on the device
+    hb = db.host
     S = hb.n_samples
-    db = eng.upload(hb)
+    rel_db = rel = None
+    if args.workload == "trainval":  # + pairwise relation table over 200 annotations per sample (BASELINE config 5)
+        ann_u = [{"point_cloud": np.zeros((0, 4), np.float32), "annotations": make_sample(base + 50000 + i, n_sweeps=1, n_boxes=200)["annotations"]}
+                 for i in range(n_unique)]
+        rel_db = eng.upload_tiled(pack_batch(ann_u), reps, S)
+        rel, _ = eng.alloc_relations(rel_db.host)
     out = eng.alloc_result(hb)
     abytes = algorithmic_bytes(hb, params)
     stream = torch.cuda.current_stream()
@@ -206,6 +226,8 @@ def main():
 
     def step():
         eng.run_fused(db, out)
+        if rel_db is not None:
+            eng.run_relations(rel_db, rel)
         if world > 1:  # NCCL only gathers the small result tables; BEV grids stay sharded
             for t, g in zip(out.table_tensors(), gathered):
                 dist.all_gather_into_tensor(g, t)
@@ -226,6 +248,8 @@ def main():
         eng.run_fused(db, out)
         kb.record(stream)
         kern_events.append((ka, kb))
+        if rel_db is not None:
+            eng.run_relations(rel_db, rel)
         if world > 1:
             for t, g in zip(out.table_tensors(), gathered):
                 dist.all_gather_into_tensor(g, t)
@@ -237,13 +261,14 @@ def main():
         t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    value = world * S * args.steps / (elapsed_ms * 1e-3)
+    total_samples = strong_total if strong_total else world * S
+    value = total_samples * args.steps / (elapsed_ms * 1e-3)
     gpu_launches = eng.kernel_launches - launches0
     kavg_ms = sum(kern_ms) / len(kern_ms)
 
     # ---------------------------------------------------------------- end to end: pinned host buffers in, host tables out
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not strong_total:
         # one chunk = one copy of the distinct-sample set (loader-format flat buffers) in pinned host memory;
         # three staging slots / streams so H2D, kernel and D2H of neighbouring chunks overlap
         n_slots = 3
@@ -310,10 +335,10 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": v1,
                "sample": f"{n_cpu} samples of the same workload, scalar C oracle (oracle/c/msc_oracle.c), {cores} threads, {dt:.1f} s wall"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong_total else "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": f"synthetic ({n_unique} distinct seeded samples per rank tiled x{reps}, distinct memory)",
-            "config": {"workload": wname, "samples_per_gpu": S, "points_per_step_per_gpu": hb.n_points,
-                       "l2_policy": "inputs (%.2f GB per step) larger than L2; no explicit flush" % (hb.points.nbytes / 1e9),
+            "config": {"workload": wname, "samples_per_gpu": S, "total_samples": total_samples, "points_per_step_per_gpu": hb.n_points,
+                       "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (hb.n_points * 20 / 1e9),
                        "fov_counts": bool(args.fov), "bev_window_cells": _capi.get_option("last_window"),
                        "tile_pts": _capi.get_option("tile_pts"), "stages": _capi.get_option("stages"),
                        "threads": _capi.get_option("threads")},

@@ -169,6 +169,11 @@ int msc_box_footprints(int32_t n, const double* boxes, const double* ego_pose, d
 int msc_relation_table(int32_t n, const double* rect, float* dist, float* bearing, uint8_t* category,
                        uint8_t* overlap, void* stream);
 
+/* Batched form: sample s owns rect rows [box_off[s], box_off[s+1]) (box_off: device i32[n_samples+1]) and writes its n_s x n_s tables
+ * at element offset pair_off[s] (device i64[n_samples]) of the four output arrays.  max_boxes = max n_s. */
+int msc_relation_table_batch(int32_t n_samples, int32_t max_boxes, const int32_t* box_off, const int64_t* pair_off, const double* rect,
+                             float* dist, float* bearing, uint8_t* category, uint8_t* overlap, void* stream);
+
 /* [EXT] standalone box -> camera projection (also fused into msc_fused_evidence_batch). */
 int msc_project_boxes(int32_t n_boxes, const double* boxes, int32_t n_cams, const double* cam_ego_pose,
                       const double* cam_calib, const double* cam_K, int32_t image_w, int32_t image_h,

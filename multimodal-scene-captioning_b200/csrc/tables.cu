@@ -50,10 +50,21 @@ __global__ void __launch_bounds__(128) box_footprints_kernel(int n, const double
 }
 
 // one thread per ordered pair; rect rows are staged through smem per 16x16 tile
-__global__ void __launch_bounds__(256) relation_table_kernel(int n, const double* __restrict__ rect, float* __restrict__ dist,
+// blockIdx.z selects the sample of a batch: sample s uses rect rows [off[s], off[s+1]) and writes its n_s x n_s tables at pair_off[s]
+__global__ void __launch_bounds__(256) relation_table_kernel(int n_single, const int32_t* __restrict__ box_off, const int64_t* __restrict__ pair_off,
+                                                            const double* __restrict__ rect, float* __restrict__ dist,
                                                             float* __restrict__ bearing, uint8_t* __restrict__ category,
                                                             uint8_t* __restrict__ overlap) {
     __shared__ double sA[16][6], sB[16][6];
+    int n = n_single;
+    if (box_off) {
+        const int s = blockIdx.z;
+        n = box_off[s + 1] - box_off[s];
+        rect += (size_t)box_off[s] * 6;
+        const size_t po = (size_t)pair_off[s];
+        dist += po; bearing += po; category += po; overlap += po;
+        if ((int)(blockIdx.x * 16) >= n || (int)(blockIdx.y * 16) >= n) return;  // whole tile outside this sample (uniform per block)
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int j = blockIdx.x * 16 + tx, i = blockIdx.y * 16 + ty;
     if (threadIdx.x < 96) {
@@ -128,7 +139,20 @@ int msc_relation_table(int32_t n, const double* rect, float* dist, float* bearin
     if (n == 0) return MSC_OK;
     MSC_REQUIRE(rect && dist && bearing && category && overlap, "null argument");
     dim3 grid((n + 15) / 16, (n + 15) / 16);
-    relation_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, rect, dist, bearing, category, overlap);
+    relation_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, nullptr, nullptr, rect, dist, bearing, category, overlap);
+    MSC_CUDA(cudaGetLastError());
+    return MSC_OK;
+}
+
+int msc_relation_table_batch(int32_t n_samples, int32_t max_boxes, const int32_t* box_off, const int64_t* pair_off, const double* rect, float* dist,
+                             float* bearing, uint8_t* category, uint8_t* overlap, void* stream) {
+    using namespace msc;
+    MSC_REQUIRE(n_samples >= 0 && max_boxes >= 0, "negative counts");
+    if (n_samples == 0 || max_boxes == 0) return MSC_OK;
+    MSC_REQUIRE(n_samples <= 65535, "at most 65535 samples per call");
+    MSC_REQUIRE(box_off && pair_off && rect && dist && bearing && category && overlap, "null argument");
+    dim3 grid((max_boxes + 15) / 16, (max_boxes + 15) / 16, n_samples);
+    relation_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(0, box_off, pair_off, rect, dist, bearing, category, overlap);
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
 }

@@ -114,6 +114,34 @@ class GeometryEngine:
             tensors[k] = src.to(self.device, non_blocking=non_blocking)
         return DeviceBatch(hb, tensors)
 
+    def upload_tiled(self, hb: HostBatch, reps: int, n_samples: Optional[int] = None) -> DeviceBatch:
+        """Upload `hb` once and replicate it `reps` times ON THE DEVICE (distinct memory, identical content), optionally keeping only
+        the first `n_samples` samples.  Host memory stays at one copy, so shards of tens of gigabytes can be built from a small pool of
+        distinct samples; the returned DeviceBatch's host side carries the metadata only (its `points` array is empty)."""
+        from .layout import tile_batch, truncate_batch
+        npad = hb.points.shape[0] - 4
+        meta_src = HostBatch(hb.n_samples, np.zeros((npad + 4, 0), np.float32), hb.sample_sweep_off, hb.sweep_start, hb.sweep_count, hb.sweep_pose,
+                             hb.sweep_time_lag, hb.sample_box_off, hb.boxes, hb.ego_pose, hb.lidar_calib, hb.cam_ego_pose, hb.cam_calib, hb.cam_K,
+                             hb.n_cams, hb.max_boxes_per_sample)
+        meta = tile_batch(meta_src, reps)
+        if n_samples is not None and n_samples < meta.n_samples:
+            meta = truncate_batch(meta, n_samples)
+        ns = meta.sweep_start.shape[0]
+        rows = int(meta.sweep_start[ns - 1] + ((int(meta.sweep_count[ns - 1]) + 3) & ~3)) if ns else 0
+        src = _as_torch_cpu(hb.points).to(self.device)
+        pts = torch.empty((rows + 4, 5), dtype=torch.float32, device=self.device)
+        pts[rows:] = float("nan")
+        for r in range((rows + npad - 1) // npad if npad else 0):
+            a = r * npad
+            b = min(a + npad, rows)
+            pts[a:b] = src[: b - a]
+        tensors = {"points": pts}
+        for k in _IN_FIELDS:
+            if k != "points":
+                tensors[k] = _as_torch_cpu(getattr(meta, k)).to(self.device)
+        meta.points = np.zeros((0, 5), np.float32)
+        return DeviceBatch(meta, tensors)
+
     @staticmethod
     def pin(hb: HostBatch) -> Dict[str, torch.Tensor]:
         return {k: _as_torch_cpu(getattr(hb, k)).pin_memory() for k in _IN_FIELDS}
@@ -146,6 +174,30 @@ class GeometryEngine:
                                                       C.c_void_p(stream)), "msc_fused_evidence_batch")
         self.kernel_launches += 3 if _capi.get_option("fov") else 2  # tables (+ wedge classes) + streaming kernel
         return out
+
+    # ------------------------------------------------------------------ batched pairwise relation tables ([EXT] e6)
+    def alloc_relations(self, hb: HostBatch):
+        """Ragged per-sample n_s x n_s tables in flat device arrays; returns (tensors dict, pair offsets on host)."""
+        nb = np.diff(hb.sample_box_off).astype(np.int64)
+        pair_off = np.zeros(hb.n_samples, np.int64)
+        pair_off[1:] = np.cumsum(nb[:-1] ** 2)
+        total = int((nb ** 2).sum())
+        d = self.device
+        return {"rect": torch.empty((hb.n_boxes, 6), dtype=torch.float64, device=d), "dist": torch.empty(total, dtype=torch.float32, device=d),
+                "bearing": torch.empty(total, dtype=torch.float32, device=d), "category": torch.empty(total, dtype=torch.uint8, device=d),
+                "overlap": torch.empty(total, dtype=torch.uint8, device=d), "pair_off": torch.from_numpy(pair_off).to(d)}, pair_off
+
+    def run_relations(self, db: DeviceBatch, rel: Dict[str, torch.Tensor]) -> None:
+        """Footprints of every box (loader's global frame, like the reference's annotation path) + one batched relation launch."""
+        hb = db.host
+        if hb.n_boxes == 0:
+            return
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(self.lib.msc_box_footprints(hb.n_boxes, db.tensors["boxes"].data_ptr(), None, rel["rect"].data_ptr(), stream), "msc_box_footprints")
+        _capi.check(self.lib.msc_relation_table_batch(hb.n_samples, hb.max_boxes_per_sample, db.tensors["sample_box_off"].data_ptr(),
+                                                      rel["pair_off"].data_ptr(), rel["rect"].data_ptr(), rel["dist"].data_ptr(), rel["bearing"].data_ptr(),
+                                                      rel["category"].data_ptr(), rel["overlap"].data_ptr(), stream), "msc_relation_table_batch")
+        self.kernel_launches += 2
 
     def process_samples(self, samples: Sequence[dict], params: Optional[GeomParams] = None) -> Dict[str, np.ndarray]:
         """Host-in / host-out convenience: pack, upload, run, download."""

@@ -170,3 +170,17 @@ def tile_batch(hb: HostBatch, reps: int) -> HostBatch:
     return HostBatch(hb.n_samples * reps, points, sso, sweep_start, t(hb.sweep_count), t(hb.sweep_pose), t(hb.sweep_time_lag), sbo,
                      t(hb.boxes), t(hb.ego_pose), t(hb.lidar_calib), t(hb.cam_ego_pose), t(hb.cam_calib), t(hb.cam_K), hb.n_cams,
                      hb.max_boxes_per_sample)
+
+
+def truncate_batch(hb: HostBatch, n: int) -> HostBatch:
+    """The first `n` samples of a packed batch (views where possible)."""
+    if n >= hb.n_samples:
+        return hb
+    ns, nb = int(hb.sample_sweep_off[n]), int(hb.sample_box_off[n])
+    end = int(hb.sweep_start[ns - 1] + ((int(hb.sweep_count[ns - 1]) + 3) & ~3)) if ns > 0 else 0
+    pts = np.concatenate([hb.points[:end], np.full((4, hb.points.shape[1]), np.nan, np.float32)], 0)
+    counts = np.diff(hb.sample_box_off[: n + 1])
+    return HostBatch(n, pts, hb.sample_sweep_off[: n + 1].copy(), hb.sweep_start[:ns].copy(), hb.sweep_count[:ns].copy(), hb.sweep_pose[:ns].copy(),
+                     hb.sweep_time_lag[:ns].copy(), hb.sample_box_off[: n + 1].copy(), hb.boxes[:nb].copy(), hb.ego_pose[:n].copy(),
+                     hb.lidar_calib[:n].copy(), hb.cam_ego_pose[:n].copy(), hb.cam_calib[:n].copy(), hb.cam_K[:n].copy(), hb.n_cams,
+                     int(counts.max()) if n > 0 else 0)

@@ -380,6 +380,44 @@ def test_projection_and_relations_match_oracle(engine):
     assert rel["overlap"].sum() > 200  # diagonal + some genuinely overlapping footprints
 
 
+def test_upload_tiled_equals_host_tiling(engine):
+    import torch
+    from msc_geom.layout import truncate_batch
+    hb_u = pack_batch([make_sample(130 + i, n_sweeps=2, n_boxes=4 + i) for i in range(3)])
+    for reps, keep in ((3, None), (3, 7), (1, 2)):
+        want = tile_batch(hb_u, reps)
+        if keep is not None:
+            want = truncate_batch(want, keep)
+        got = engine.upload_tiled(hb_u, reps, keep)
+        assert got.host.n_samples == want.n_samples and got.host.n_points == want.n_points
+        for k in ("sample_sweep_off", "sweep_start", "sweep_count", "sweep_pose", "sample_box_off", "boxes", "cam_K"):
+            assert np.array_equal(got.tensors[k].cpu().numpy().view(getattr(want, k).dtype).reshape(getattr(want, k).shape), getattr(want, k)), k
+        assert np.array_equal(got.tensors["points"].cpu().numpy(), want.points, equal_nan=True)
+        a = engine.run_fused(got); torch.cuda.synchronize(); a = a.to_host()
+        b = engine.run_fused(engine.upload(want)); torch.cuda.synchronize(); b = b.to_host()
+        for k in ("box_count", "bev_count", "stats", "box_centroid"):
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_batched_relation_tables_match_oracle(engine):
+    import torch
+    samples = [make_sample(120 + i, n_sweeps=1, n_boxes=nb) for i, nb in enumerate([7, 0, 200, 33])]
+    hb = pack_batch(samples)
+    db = engine.upload(hb)
+    rel, pair_off = engine.alloc_relations(hb)
+    engine.run_relations(db, rel); torch.cuda.synchronize()
+    for i, s in enumerate(samples):
+        n = len(s["annotations"])
+        if n == 0:
+            continue
+        ref = OB.oracle_relations(OB.oracle_footprints(boxes_from_annotations(s["annotations"]), None))
+        sl = slice(int(pair_off[i]), int(pair_off[i]) + n * n)
+        assert np.array_equal(rel["dist"][sl].cpu().numpy().reshape(n, n), ref["dist"])
+        assert np.array_equal(rel["category"][sl].cpu().numpy().reshape(n, n), ref["category"])
+        assert np.array_equal(rel["overlap"][sl].cpu().numpy().reshape(n, n), ref["overlap"])
+        assert np.allclose(rel["bearing"][sl].cpu().numpy().reshape(n, n), ref["bearing"], rtol=1e-5, atol=1e-4)
+
+
 def test_patch_reference_style_classes(engine, golden_dir):
     """integration.patch_reference() on stand-ins shaped like the reference classes (same attribute names)."""
     from msc_geom import integration
