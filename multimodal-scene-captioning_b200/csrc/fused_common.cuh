@@ -1,0 +1,149 @@
+// fused_common.cuh -- types and device helpers shared by the two generations of the streaming kernel
+// (fused_evidence.cu: configs 0-6; fused_stream.cu: config 7, the default).
+#pragma once
+#include "msc_common.cuh"
+
+namespace msc {
+
+constexpr int kMaxSweepsSmem = 64;  // per-sample sweep table cached in smem (larger samples read it from global)
+constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes the four LDS.128 conflict-free
+
+constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
+constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
+constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs; the odd
+                                              // stride spreads the same word of different boxes over all 32 banks
+constexpr int kMaxWarps = 32;
+
+struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
+    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, misc_off, queue_off, total_bytes;
+    int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
+    int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
+    int32_t max_boxes;             // capacity of the smem box tables
+};
+
+struct FusedArgs {
+    msc_params P;
+    msc_batch_in in;
+    msc_batch_out out;
+    FusedLayout L;
+    // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
+    float two_r, resf, rcp_two_r, cscale, iscale;
+    int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
+    uint32_t debug_skip;    // profiling only (option "debug_skip"): 1 global atomics, 2 box loop, 4 window atomics, 8 box accumulate
+};
+
+// BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
+// sequence, which tools/markstein_check.c proves equal to RN(a/b) for every float a outside the subnormal
+// quotient range for the whitelisted divisors (a = fl(c + r) is 0 or >= 2^-24 r here).
+template <bool FASTDIV>
+__device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp_two_r, float resf, int res_m1) {
+    const float a = __fadd_rn(c, r);
+    float q;
+    if (FASTDIV) {
+        const float q0 = __fmul_rn(a, rcp_two_r);
+        const float rem = __fmaf_rn(-two_r, q0, a);
+        q = __fmaf_rn(rem, rcp_two_r, q0);
+    } else {
+        q = __fdiv_rn(a, two_r);
+    }
+    const int i = __float2int_rz(__fmul_rn(q, resf));
+    return min(max(i, 0), res_m1);
+}
+
+struct TableLayout {  // offsets (bytes) into the workspace
+    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, total;
+};
+
+// fused_stream.cu (configs 7-9): bytes of its per-CTA state block, and its launcher
+int stream_misc_bytes();
+void stream_shape_info(int shape, int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
+int launch_stream_kernel(int shape, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast,
+                         cudaStream_t stream);
+
+// exact wedge test (the definition): q = p - apex, cross(e_right, q) >= 0 and cross(q, e_left) >= 0
+__device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
+    const float qx = __fsub_rn(x, wq[0]), qy = __fsub_rn(y, wq[1]);
+    const float cr = __fmaf_rn(wq[4], qy, -__fmul_rn(wq[5], qx));
+    const float cl = __fmaf_rn(qx, wq[3], -__fmul_rn(qy, wq[2]));
+    return (cr >= 0.0f) && (cl >= 0.0f);
+}
+
+// Conservative oriented rasterisation of a prepared box's xy footprint (a zonotope spanned by the projected edge
+// vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the 2 mm
+// margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
+static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint2* __restrict__ cull) {
+    const msc_params& P = A.P;
+    const FusedLayout& L = A.L;
+    const float margin = 2e-3f;
+    const float cx = o[16], cy = o[17];
+    const float ex[3] = {o[3], o[6], o[9]}, ey[3] = {o[4], o[7], o[10]};
+    const float rx = 0.5f * (fabsf(ex[0]) + fabsf(ex[1]) + fabsf(ex[2])) + margin;
+    const float ry = 0.5f * (fabsf(ey[0]) + fabsf(ey[1]) + fabsf(ey[2])) + margin;
+    const int res_m1 = P.bev_res - 1;
+    const int cx0 = bev_cell<false>(cx - rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cx1 = bev_cell<false>(cx + rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy0 = bev_cell<false>(cy - ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
+    const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
+    const int last = L.cull_dim - 1;
+    for (int gy = cy0; gy <= cy1; ++gy) {
+        for (int gx = cx0; gx <= cx1; ++gx) {
+            // edge cells absorb everything clipped into them: never reject those
+            bool reject = false;
+            if (gx > 0 && gx < last && gy > 0 && gy < last) {
+                const float mx = -P.bev_range + ((float)gx + 0.5f) * cell_m, my = -P.bev_range + ((float)gy + 0.5f) * cell_m;
+                const float dx = cx - mx, dy = cy - my;
+                const float hc = 0.5f * cell_m + margin;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float nx = -ey[k], ny = ex[k];  // normal of projected edge k
+                    const float nn = fabsf(nx) + fabsf(ny);
+                    if (nn > 1e-6f) {
+                        const float dist = fabsf(dx * nx + dy * ny);
+                        float rb = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) rb += 0.5f * fabsf(ex[j] * nx + ey[j] * ny);
+                        if (dist > (rb + hc * nn) * 1.0001f + margin * nn) reject = true;
+                    }
+                }
+            }
+            if (reject) continue;
+            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
+            for (;;) {
+                const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
+                if (old == kCullAll) break;
+                uint32_t nw = kCullAll;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (nw == kCullAll && ((old >> (8 * k)) & 0xffu) == 0xffu) nw = (old & ~(0xffu << (8 * k))) | ((uint32_t)b << (8 * k));
+                if (atomicCAS(slot, old, nw) == old) break;
+            }
+        }
+    }
+}
+
+// A.2 exact membership test of one point against one prepared box (closed intervals, float32 with fmaf chains).
+__device__ __forceinline__ bool box_contains(const float* __restrict__ boxp, int b, float xr, float yr, float zr) {
+    const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
+    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+    const float v0 = __fsub_rn(xr, b0.x), v1 = __fsub_rn(yr, b0.y), v2 = __fsub_rn(zr, b0.z);
+    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
+    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
+    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
+    return iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z;
+}
+// Accumulator update of a member point.  Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis,
+// every update a fire-and-forget ATOMS (order-independent, bit-reproducible).
+__device__ __forceinline__ void box_accumulate(const FusedArgs& A, uint32_t* __restrict__ boxacc, int b, float xr, float yr, float zr, float s2) {
+    uint32_t* acc = boxacc + b * kAccWords;
+    atomicAdd(acc + 0, 1u);
+    atomicMin(acc + 1, __float_as_uint(s2));
+    const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
+    const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
+    const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
+    atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
+    atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
+    atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
+}
+
+}  // namespace msc

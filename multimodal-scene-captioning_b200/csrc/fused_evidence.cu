@@ -21,7 +21,7 @@
 //   * per-box accumulators are smem-resident integers: count, min s, and centroid sums split into three
 //     9-bit limbs per axis so every update is a fire-and-forget ATOMS (order-independent, bit-reproducible);
 //   * no tensor cores: nothing here is a contraction.
-#include "msc_common.cuh"
+#include "fused_common.cuh"
 
 namespace msc {
 
@@ -43,32 +43,6 @@ struct Cfg {
     static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
     static_assert(STAGES >= 2 && STAGES <= 8, "ring depth");
 };
-constexpr int kMaxSweepsSmem = 64;  // per-sample sweep table cached in smem (larger samples read it from global)
-constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes the four LDS.128 conflict-free
-
-constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
-constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
-constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs; the odd
-                                              // stride spreads the same word of different boxes over all 32 banks
-constexpr int kMaxWarps = 32;
-
-struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
-    int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, misc_off, queue_off, total_bytes;
-    int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
-    int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
-    int32_t max_boxes;             // capacity of the smem box tables
-};
-
-struct FusedArgs {
-    msc_params P;
-    msc_batch_in in;
-    msc_batch_out out;
-    FusedLayout L;
-    // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
-    float two_r, resf, rcp_two_r, cscale, iscale;
-    int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
-    uint32_t debug_skip;    // profiling only (option "debug_skip"): 1 global atomics, 2 box loop, 4 window atomics, 8 box accumulate
-};
 
 struct Misc {  // small per-CTA state at misc_off
     uint64_t full_bar[kMaxWarps * 8];  // [warp][stage]: TMA bytes landed in that warp's ring slot
@@ -86,39 +60,12 @@ __device__ __forceinline__ void ld_pose(const double* __restrict__ p, double M[1
     for (int i = 0; i < 12; i += 2)
         asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(M[i]), "=d"(M[i + 1]) : "l"(p + i));
 }
-// BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
-// sequence, which tools/markstein_check.c proves equal to RN(a/b) for every float a outside the subnormal
-// quotient range for the whitelisted divisors (a = fl(c + r) is 0 or >= 2^-24 r here).
-template <bool FASTDIV>
-__device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp_two_r, float resf, int res_m1) {
-    const float a = __fadd_rn(c, r);
-    float q;
-    if (FASTDIV) {
-        const float q0 = __fmul_rn(a, rcp_two_r);
-        const float rem = __fmaf_rn(-two_r, q0, a);
-        q = __fmaf_rn(rem, rcp_two_r, q0);
-    } else {
-        q = __fdiv_rn(a, two_r);
-    }
-    const int i = __float2int_rz(__fmul_rn(q, resf));
-    return min(max(i, 0), res_m1);
-}
 
 // ------------------------------------------------------------------------------------------------ table kernel
 // Everything that does not touch points runs once per batch in a small, fully parallel kernel and lands in the
 // workspace: prepared boxes (devkit points_in_box vectors, App. A.2), box -> camera projection (A.3), camera
 // wedges, and the per-cull-cell wedge classes.  The streaming kernel then only copies its sample's rows to smem.
-struct TableLayout {  // offsets (bytes) into the workspace
-    size_t counter_off, boxprep_off, wedge_off, fovcls_off, total;
-};
 
-// exact wedge test (the definition): q = p - apex, cross(e_right, q) >= 0 and cross(q, e_left) >= 0
-__device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
-    const float qx = __fsub_rn(x, wq[0]), qy = __fsub_rn(y, wq[1]);
-    const float cr = __fmaf_rn(wq[4], qy, -__fmul_rn(wq[5], qx));
-    const float cl = __fmaf_rn(qx, wq[3], -__fmul_rn(qy, wq[2]));
-    return (cr >= 0.0f) && (cl >= 0.0f);
-}
 
 // classify one cull cell against one wedge: bit0 = every point of the cell is inside, bit1 = undecided
 __device__ __forceinline__ uint32_t classify_cell(const float* __restrict__ wq, float x0, float x1, float y0, float y1) {
@@ -136,6 +83,23 @@ __device__ __forceinline__ uint32_t classify_cell(const float* __restrict__ wq, 
     if (cr_min > guard && cl_min > guard) return 1u;    // inside
     if (cr_max < -guard || cl_max < -guard) return 0u;  // outside
     return 2u;                                          // straddling: run the exact test per point
+}
+
+// Per-edge classes of one cull cell against one wedge (fused_stream.cu): bit0 = the wedge may contain points of the cell,
+// bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same corner extremes and guard band as
+// classify_cell(); an edge every point of the cell passes needs no exact test, an edge every point fails empties the wedge.
+__device__ __forceinline__ uint32_t classify_cell_edges(const float* __restrict__ wq, float x0, float x1, float y0, float y1) {
+    const float guard = 2e-3f;
+    float cr_min = INFINITY, cr_max = -INFINITY, cl_min = INFINITY, cl_max = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float qx = ((k & 1) ? x1 : x0) - wq[0], qy = ((k & 2) ? y1 : y0) - wq[1];
+        const float cr = wq[4] * qy - wq[5] * qx, cl = qx * wq[3] - qy * wq[2];
+        cr_min = fminf(cr_min, cr); cr_max = fmaxf(cr_max, cr);
+        cl_min = fminf(cl_min, cl); cl_max = fmaxf(cl_max, cl);
+    }
+    if (cr_max < -guard || cl_max < -guard) return 0u;  // outside
+    return 1u | ((cr_min > guard) ? 0u : 2u) | ((cl_min > guard) ? 0u : 4u);
 }
 
 // camera wedge: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W (f64, no FMA)
@@ -238,92 +202,18 @@ __global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant
     const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
     const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
     const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
-    uint32_t bits = 0;
+    uint32_t bits = 0, ebits = 0;
     for (int c = 0; c < n_cams; ++c) {
         const uint32_t k = classify_cell(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
         bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
+        const uint32_t e = classify_cell_edges(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
+        ebits |= ((e & 1u) << c) | (((e >> 1) & 1u) << (8 + c)) | (((e >> 2) & 1u) << (16 + c));  // in-bit, right / left edge undecided
     }
     fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
+    reinterpret_cast<uint32_t*>(ws + T.edgecls_off)[(size_t)sample * ncc + i] = ebits;
 }
 
 // ------------------------------------------------------------------------------------------------ streaming kernel
-// Conservative oriented rasterisation of a prepared box's xy footprint (a zonotope spanned by the projected edge
-// vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the 2 mm
-// margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
-__device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint2* __restrict__ cull) {
-    const msc_params& P = A.P;
-    const FusedLayout& L = A.L;
-    const float margin = 2e-3f;
-    const float cx = o[16], cy = o[17];
-    const float ex[3] = {o[3], o[6], o[9]}, ey[3] = {o[4], o[7], o[10]};
-    const float rx = 0.5f * (fabsf(ex[0]) + fabsf(ex[1]) + fabsf(ex[2])) + margin;
-    const float ry = 0.5f * (fabsf(ey[0]) + fabsf(ey[1]) + fabsf(ey[2])) + margin;
-    const int res_m1 = P.bev_res - 1;
-    const int cx0 = bev_cell<false>(cx - rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cx1 = bev_cell<false>(cx + rx, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cy0 = bev_cell<false>(cy - ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
-    const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
-    const int last = L.cull_dim - 1;
-    for (int gy = cy0; gy <= cy1; ++gy) {
-        for (int gx = cx0; gx <= cx1; ++gx) {
-            // edge cells absorb everything clipped into them: never reject those
-            bool reject = false;
-            if (gx > 0 && gx < last && gy > 0 && gy < last) {
-                const float mx = -P.bev_range + ((float)gx + 0.5f) * cell_m, my = -P.bev_range + ((float)gy + 0.5f) * cell_m;
-                const float dx = cx - mx, dy = cy - my;
-                const float hc = 0.5f * cell_m + margin;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float nx = -ey[k], ny = ex[k];  // normal of projected edge k
-                    const float nn = fabsf(nx) + fabsf(ny);
-                    if (nn > 1e-6f) {
-                        const float dist = fabsf(dx * nx + dy * ny);
-                        float rb = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) rb += 0.5f * fabsf(ex[j] * nx + ey[j] * ny);
-                        if (dist > (rb + hc * nn) * 1.0001f + margin * nn) reject = true;
-                    }
-                }
-            }
-            if (reject) continue;
-            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
-            for (;;) {
-                const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
-                if (old == kCullAll) break;
-                uint32_t nw = kCullAll;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (nw == kCullAll && ((old >> (8 * k)) & 0xffu) == 0xffu) nw = (old & ~(0xffu << (8 * k))) | ((uint32_t)b << (8 * k));
-                if (atomicCAS(slot, old, nw) == old) break;
-            }
-        }
-    }
-}
-
-// A.2 exact membership test of one point against one prepared box (closed intervals, float32 with fmaf chains).
-__device__ __forceinline__ bool box_contains(const float* __restrict__ boxp, int b, float xr, float yr, float zr) {
-    const float4* bp = reinterpret_cast<const float4*>(boxp + b * kBoxStride);
-    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-    const float v0 = __fsub_rn(xr, b0.x), v1 = __fsub_rn(yr, b0.y), v2 = __fsub_rn(zr, b0.z);
-    const float iv = __fmaf_rn(b1.y, v2, __fmaf_rn(b1.x, v1, __fmul_rn(b0.w, v0)));
-    const float jv = __fmaf_rn(b2.x, v2, __fmaf_rn(b1.w, v1, __fmul_rn(b1.z, v0)));
-    const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
-    return iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z;
-}
-// Accumulator update of a member point.  Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis,
-// every update a fire-and-forget ATOMS (order-independent, bit-reproducible).
-__device__ __forceinline__ void box_accumulate(const FusedArgs& A, uint32_t* __restrict__ boxacc, int b, float xr, float yr, float zr, float s2) {
-    uint32_t* acc = boxacc + b * kAccWords;
-    atomicAdd(acc + 0, 1u);
-    atomicMin(acc + 1, __float_as_uint(s2));
-    const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
-    const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
-    const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
-    atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
-    atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
-    atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
-}
 
 template <class C, bool FOV, bool FASTDIV>
 __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
@@ -730,11 +620,12 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes)
     T.boxprep_off = off; off = align(off + (size_t)(n_boxes > 0 ? n_boxes : 1) * kBoxStride * 4);
     T.wedge_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * MSC_MAX_CAMS * 6 * 4);
     T.fovcls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 2);
+    T.edgecls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 4);
     T.total = off;
     return T;
 }
 
-static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, int queue_bytes, FusedLayout* L) {
+static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, int queue_bytes, int misc_bytes, FusedLayout* L) {
     const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
     cull_geometry(P, &L->cull_shift, &L->cull_dim);
     L->max_boxes = cap;
@@ -744,7 +635,7 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
     L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
-    L->misc_off = off; off += (int)((sizeof(Misc) + 127) & ~127);
+    L->misc_off = off; off += (misc_bytes + 127) & ~127;
     L->window_off = off;
     const int avail = smem_limit - off;
     if (avail < 0) return -1;
@@ -767,17 +658,8 @@ static int launch_fused(const FusedArgs& args, const TableLayout& T, unsigned ch
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
 }
-template <class C>
-static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid, bool fov,
-                          bool fast, cudaStream_t stream) {
-    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, C::kQueueBytes, &args.L) != 0) {
-        set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
-        return MSC_ERR_UNSUPPORTED;
-    }
-    g_last_window = args.L.win_w;
-    g_last_smem = args.L.total_bytes;
-    g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
-    // (1) tables: prepared boxes, projection, wedges, wedge classes
+// tables (prepared boxes, projection, wedges, wedge classes -> workspace), launched before either streaming kernel
+static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, bool fov, cudaStream_t stream) {
     const int ncc = args.L.cull_dim * args.L.cull_dim;
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
@@ -791,9 +673,40 @@ static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* 
         fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
     }
-    // (2) the streaming pass
+    return MSC_OK;
+}
+
+template <class C>
+static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid, bool fov,
+                          bool fast, cudaStream_t stream) {
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, C::kQueueBytes, (int)sizeof(Misc), &args.L) != 0) {
+        set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
+        return MSC_ERR_UNSUPPORTED;
+    }
+    g_last_window = args.L.win_w;
+    g_last_smem = args.L.total_bytes;
+    g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
+    const int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    if (rc != MSC_OK) return rc;
     if (fov) return fast ? launch_fused<C, true, true>(args, T, ws, grid, stream) : launch_fused<C, true, false>(args, T, ws, grid, stream);
     return fast ? launch_fused<C, false, true>(args, T, ws, grid, stream) : launch_fused<C, false, false>(args, T, ws, grid, stream);
+}
+
+// configs 7-9: the second-generation streaming kernel (fused_stream.cu), launch shapes 0-2
+static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid,
+                           bool fov, bool fast, cudaStream_t stream) {
+    int threads = 0, tile_pts = 0, ring = 0, queue = 0;
+    stream_shape_info(shape, &threads, &tile_pts, &ring, &queue);
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, ring, queue, stream_misc_bytes(), &args.L) != 0) {
+        set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
+        return MSC_ERR_UNSUPPORTED;
+    }
+    g_last_window = args.L.win_w;
+    g_last_smem = args.L.total_bytes;
+    g_last_tile_pts = tile_pts; g_last_stages = 2; g_last_threads = threads;
+    const int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    if (rc != MSC_OK) return rc;
+    return launch_stream_kernel(shape, args, T, ws, grid, fov, fast, stream);
 }
 
 }  // namespace msc
@@ -875,6 +788,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     MSC_CUDA(cudaMemsetAsync(ws + T.counter_off, 0, 256, stream));
     const int grid = in->n_samples < sms ? in->n_samples : sms;
     switch (g_opt_config) {
+        case 7: case 8: case 9: return dispatch_stream(g_opt_config - 7, args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 3: return dispatch_fused<Cfg<512, 4, 2>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);

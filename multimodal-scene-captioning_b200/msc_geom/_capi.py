@@ -100,6 +100,9 @@ def load():
     return lib
 
 
+DEFAULT_FUSED_CONFIG = 6  # launch shape the library selects by default (fused_evidence.cu: g_opt_config)
+
+
 def check(status: int, what: str):
     if status != 0:
         msg = load().msc_last_error().decode("utf-8", "replace")

@@ -18,7 +18,16 @@ from tests import oracle_bridge as OB
 IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
 
 
-def check_fused(eng, samples, params=None, config=6, n_cams=6):
+DEFAULT_CONFIGS = (6, 7, 9)  # first-generation kernel, second-generation kernel (1024 x 2 and 512 x 4 launch shapes)
+
+
+def check_fused(eng, samples, params=None, config=None, n_cams=6):
+    """Run the fused path and compare every output with the oracle; config=None checks every shape in DEFAULT_CONFIGS."""
+    if config is None:
+        for cfg in DEFAULT_CONFIGS:
+            res = check_fused(eng, samples, params=params, config=cfg, n_cams=n_cams)
+        _capi.set_option("config", _capi.DEFAULT_FUSED_CONFIG)
+        return res
     p = params or GeomParams()
     _capi.set_option("config", config)
     hb = pack_batch(samples, n_cams=n_cams)
@@ -30,17 +39,17 @@ def check_fused(eng, samples, params=None, config=6, n_cams=6):
         ref = OB.oracle_fused(hb, i, p)
         b0, b1 = hb.sample_box_off[i], hb.sample_box_off[i + 1]
         for k in ("box_count", "box_nearest", "box_centroid", "proj_visible", "proj_extent"):
-            assert np.array_equal(got[k][b0:b1], ref[k], equal_nan=True), (i, k)
+            assert np.array_equal(got[k][b0:b1], ref[k], equal_nan=True), (config, i, k)
         for k in ("bev_count", "bev_isum_q", "bev_height"):
-            assert np.array_equal(got[k][i], ref[k]), (i, k, int((got[k][i] != ref[k]).sum()))
-        assert np.array_equal(got["stats"][i][:13], ref["stats"][:13]), (i, got["stats"][i], ref["stats"])
+            assert np.array_equal(got[k][i], ref[k]), (config, i, k, int((got[k][i] != ref[k]).sum()))
+        assert np.array_equal(got["stats"][i][:13], ref["stats"][:13]), (config, i, got["stats"][i], ref["stats"])
         # size-independent invariants
         st = got["stats"][i]
         assert st[3] + st[4] == st[2] and int(got["bev_count"][i].sum()) == st[2] and st[1] <= st[0]
     return hb, got
 
 
-@pytest.mark.parametrize("config", [0, 2, 3, 6])
+@pytest.mark.parametrize("config", [0, 2, 3, 6, 7, 8, 9])
 def test_fused_config3_shape(engine, config):
     check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
 
@@ -60,7 +69,7 @@ def test_fused_ragged_and_empty_inputs(engine):
     c = make_sample(32, n_sweeps=1, n_boxes=3)
     c["lidar_sweeps"] = [dict(c["lidar_sweeps"][0], points_raw=c["lidar_sweeps"][0]["points_raw"][:0])]  # no points at all
     d = {"point_cloud": np.random.default_rng(5).normal(0, 12, (5000, 4)).astype(np.float32), "annotations": []}  # plain reference-style sample
-    for cfg in (1, 2, 6):
+    for cfg in (1, 2, 6, 7, 8, 9):
         check_fused(engine, [a, b, c, d], config=cfg)
 
 
@@ -130,7 +139,7 @@ def test_fused_many_sweeps_and_camera_counts(engine):
         M[:, 3] += 0.01 * k                         # every sweep gets its own transform
         sw.append(dict(src, points_raw=src["points_raw"][k * 97: k * 97 + 700 + 13 * k], ref_from_sensor=M))
     many = dict(base, lidar_sweeps=sw)
-    for cfg in (0, 6):
+    for cfg in (0, 6, 7, 8, 9):
         check_fused(engine, [many, make_sample(96, n_sweeps=2, n_boxes=5)], config=cfg)
     s0 = make_sample(97, n_sweeps=2, n_boxes=9)
     s0["cameras"] = []
@@ -159,12 +168,13 @@ def test_fused_fov_counts_off_and_small_window(engine):
     _capi.set_option("window", 0)
 
 
-def test_fused_full_size_batch_properties(engine):
+@pytest.mark.parametrize("config", [6, 7])
+def test_fused_full_size_batch_properties(engine, config):
     """BASELINE config-3 batch at the benchmark's size (592 samples, 205.5 M points): size-independent properties, replica
     equality (bit-reproducibility under different scheduling), idempotence, and the oracle on sampled samples."""
     import torch
     p = GeomParams()
-    _capi.set_option("config", 6)
+    _capi.set_option("config", config)
     uniq = [make_sample(100 + i, n_sweeps=10, n_boxes=60) for i in range(8)]
     hb_u = pack_batch(uniq)
     hb = tile_batch(hb_u, 74)
