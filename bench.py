@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fov", type=int, default=1)
     ap.add_argument("--window", type=int, default=0)
-    ap.add_argument("--config", type=int, default=6, help="launch shape of the fused kernel (see msc_fused_set_option)")
+    ap.add_argument("--config", type=int, default=7, help="launch shape of the fused kernel (see msc_fused_set_option)")
     ap.add_argument("--cull-shift", type=int, default=-1)
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: knock out stages of the fused kernel (results invalid)")
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")

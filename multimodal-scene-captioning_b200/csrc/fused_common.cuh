@@ -51,7 +51,7 @@ __device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp
 }
 
 struct TableLayout {  // offsets (bytes) into the workspace
-    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, total;
+    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, cullids_off, total;
 };
 
 // fused_stream.cu (configs 7-9): bytes of its per-CTA state block, and its launcher
@@ -71,7 +71,9 @@ __device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, 
 // Conservative oriented rasterisation of a prepared box's xy footprint (a zonotope spanned by the projected edge
 // vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the 2 mm
 // margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
-static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint2* __restrict__ cull) {
+// cull_words: first id word of cell 0; STRIDE words between cells (2: the smem (ids, classes) pairs, 1: the workspace id table).
+template <int STRIDE>
+static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint32_t* __restrict__ cull_words) {
     const msc_params& P = A.P;
     const FusedLayout& L = A.L;
     const float margin = 2e-3f;
@@ -108,7 +110,7 @@ static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const floa
                 }
             }
             if (reject) continue;
-            uint32_t* slot = &cull[gy * L.cull_dim + gx].x;
+            uint32_t* slot = cull_words + (size_t)(gy * L.cull_dim + gx) * STRIDE;
             for (;;) {
                 const uint32_t old = *reinterpret_cast<volatile uint32_t*>(slot);
                 if (old == kCullAll) break;

@@ -213,6 +213,21 @@ __global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant
     reinterpret_cast<uint32_t*>(ws + T.edgecls_off)[(size_t)sample * ncc + i] = ebits;
 }
 
+// Candidate-box ids per (sample, cull cell) for fused_stream.cu: the same conservative rasterisation the first-generation kernel
+// runs inside its per-sample prologue, one thread per box, into a workspace table the host pre-fills with kCullEmpty.
+__global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
+                                                           unsigned char* __restrict__ ws) {
+    const int gb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= n_boxes_total) return;
+    int lo = 0, hi = A.in.n_samples;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.in.sample_box_off[mid] <= gb) lo = mid; else hi = mid; }
+    const int b = gb - A.in.sample_box_off[lo];
+    if (b >= A.L.max_boxes) return;  // caller under-declared max_boxes_per_sample: the streaming kernel drops these boxes too
+    const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)gb * kBoxStride;
+    uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off) + (size_t)lo * (size_t)(A.L.cull_dim * A.L.cull_dim);
+    rasterise_box<1>(A, o, b, ids);
+}
+
 // ------------------------------------------------------------------------------------------------ streaming kernel
 
 template <class C, bool FOV, bool FASTDIV>
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) fused_evidence_kernel(const __
         }
         __threadfence();
         __syncthreads();
-        for (int b = tid; b < n_boxes; b += NT) rasterise_box(A, boxp + b * kBoxStride, b, cull);
+        for (int b = tid; b < n_boxes; b += NT) rasterise_box<2>(A, boxp + b * kBoxStride, b, reinterpret_cast<uint32_t*>(cull));
         __syncthreads();
 
         // ------------------------------------------------------------ main loop: this warp's tiles, no cross-warp sync
@@ -588,8 +603,9 @@ static int g_opt_window = 0;       // 0 = auto (largest that fits)
 static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
 static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
 static int g_opt_debug_skip = 0;
-static int g_opt_config = 6;  // launch shape (threads x points per lane, ring stages): 0 = 512x2,4; 1 = 512x2,3; 2 = 1024x2,2 pose in smem;
-                              // 3 = 512x4,2; 4 = 768x2,3; 5 = 1024x1,4; 6 = shape 2 + per-warp candidate queue (default)
+static int g_opt_config = 7;  // launch shape: 7 = second-generation kernel (fused_stream.cu), 1024 threads x 2 points per lane (default);
+                              // 8 = the same kernel with 512 threads x 4 points per lane; first generation (this file): 0 = 512x2,4 ring
+                              // stages; 1 = 512x2,3; 2 = 1024x2,2 pose in smem; 3 = 512x4,2; 4 = 768x2,3; 5 = 1024x1,4; 6 = shape 2 + candidate queue
 static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 
 // divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
@@ -621,6 +637,7 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes)
     T.wedge_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * MSC_MAX_CAMS * 6 * 4);
     T.fovcls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 2);
     T.edgecls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 4);
+    T.cullids_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 4);
     T.total = off;
     return T;
 }
@@ -692,7 +709,7 @@ static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* 
     return fast ? launch_fused<C, false, true>(args, T, ws, grid, stream) : launch_fused<C, false, false>(args, T, ws, grid, stream);
 }
 
-// configs 7-9: the second-generation streaming kernel (fused_stream.cu), launch shapes 0-2
+// configs 7-8: the second-generation streaming kernel (fused_stream.cu), launch shapes 0-1
 static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid,
                            bool fov, bool fast, cudaStream_t stream) {
     int threads = 0, tile_pts = 0, ring = 0, queue = 0;
@@ -706,6 +723,12 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
     g_last_tile_pts = tile_pts; g_last_stages = 2; g_last_threads = threads;
     const int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
     if (rc != MSC_OK) return rc;
+    const size_t ncc = (size_t)args.L.cull_dim * args.L.cull_dim;
+    MSC_CUDA(cudaMemsetAsync(ws + T.cullids_off, 0xff, (size_t)args.in.n_samples * ncc * 4, stream));  // kCullEmpty
+    if (n_boxes_total > 0) {
+        fused_cullids_kernel<<<(unsigned)((n_boxes_total + 127) / 128), 128, 0, stream>>>(args, T, n_boxes_total, ws);
+        MSC_CUDA(cudaGetLastError());
+    }
     return launch_stream_kernel(shape, args, T, ws, grid, fov, fast, stream);
 }
 
@@ -788,7 +811,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     MSC_CUDA(cudaMemsetAsync(ws + T.counter_off, 0, 256, stream));
     const int grid = in->n_samples < sms ? in->n_samples : sms;
     switch (g_opt_config) {
-        case 7: case 8: case 9: return dispatch_stream(g_opt_config - 7, args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
+        case 7: case 8: return dispatch_stream(g_opt_config - 7, args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 3: return dispatch_fused<Cfg<512, 4, 2>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);

@@ -60,7 +60,7 @@ __device__ __forceinline__ void lds_f64x2(uint32_t saddr, double& a, double& b) 
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(saddr));
 }
 
-template <class C, bool FOV, bool FASTDIV>
+template <class C, bool FOV, bool FASTDIV, bool KEEPMASK>
 __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
                                                                          unsigned char* __restrict__ ws) {
     constexpr int NT = C::kThreads, W = C::kWarps, PPT = C::kPts, TP = C::kTilePts, TF = C::kTileFloats;
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     const float* const g_boxprep = reinterpret_cast<const float*>(ws + T.boxprep_off);
     const float* const g_wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
     const uint32_t* const g_edgecls = reinterpret_cast<const uint32_t*>(ws + T.edgecls_off);
+    const uint32_t* const g_cullids = reinterpret_cast<const uint32_t*>(ws + T.cullids_off);
 
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform as far as the compiler is concerned
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     const size_t ncell = (size_t)res * (size_t)res;
     const int n_cams = P.n_cams;
     const uint64_t policy = l2_policy_evict_first();
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t lt_mask = (1u << lane) - 1u;
+    asm volatile("" : "+r"(lt_mask));  // keep it in its register (the compiler would re-derive it from %tid at every use)
 
     if (lane == 0) {
         mbar_init(&misc->full_bar[warp * 2 + 0], 1);
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
             for (int i = tid; i < n_w4; i += NT) w4[i] = make_uint4(0, 0, 0, 0);
             const int n_cull = L.cull_dim * L.cull_dim;
             const uint32_t* ec = g_edgecls + (size_t)sample * n_cull;
-            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(kCullEmpty, (FOV && n_cams > 0) ? ec[i] : 0u);
+            const uint32_t* ids = g_cullids + (size_t)sample * n_cull;  // candidate boxes per cull cell (fused_cullids_kernel)
+            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(ids[i], (FOV && n_cams > 0) ? ec[i] : 0u);
             for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
             const float4* bsrc = reinterpret_cast<const float4*>(g_boxprep + (size_t)bx0 * kBoxStride);
             for (int i = tid; i < n_boxes * (kBoxStride / 4); i += NT) reinterpret_cast<float4*>(boxp)[i] = bsrc[i];
@@ -191,8 +194,6 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
             for (size_t i = tid; i < ncell / 4; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
         }
         __threadfence();
-        __syncthreads();
-        for (int b = tid; b < n_boxes; b += NT) rasterise_box(A, boxp + b * kBoxStride, b, cull);
         __syncthreads();
 
         // ------------------------------------------------------------ main loop: this warp's tiles, no cross-warp sync
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     const float x = tp[u * 160 + 0], y = tp[u * 160 + 1], z = tp[u * 160 + 2];
                     inten[u] = tp[u * 160 + 3];
                     // A.1 remove_close (square, sweep's own sensor frame)
-                    keep[u] = valid && !(fabsf(x) < P.remove_close_radius && fabsf(y) < P.remove_close_radius);
+                    const bool close = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
+                    keep[u] = valid & !close;
                     xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
                     c_close += keep[u] ? 1u : 0u;
                 }
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     // spread 8 bits into 8 byte counters (no carries: the multiplier's partial products do not overlap)
                     cam_lo += ((in_bits[u] & 0xfu) * 0x00204081u) & 0x01010101u;
                     cam_hi += ((in_bits[u] >> 4) * 0x00204081u) & 0x01010101u;
-                    if (P.fov_keep_mask != 0u && (in_bits[u] & P.fov_keep_mask) == 0u) keep[u] = false;
+                    if (KEEPMASK && (in_bits[u] & P.fov_keep_mask) == 0u) keep[u] = false;  // fov_keep_mask != 0: a FOV filter, not only counts
                 }
                 c_kept += keep[u] ? 1u : 0u;
                 c_ground += (keep[u] && zr[u] < P.ground_z) ? 1u : 0u;  // lidar_agent.py:128
@@ -404,7 +406,6 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
             for (int u = 0; u < PPT; ++u) {
                 const bool has = cand[u] != kCullEmpty;
                 const uint32_t m = __ballot_sync(0xffffffffu, has);
-                if (m == 0u) continue;
                 if (has) {
                     const uint32_t slot = (q_tail + __popc(m & lt_mask)) & 63u;
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(queue_s + (slot << 4)), "f"(xr[u]), "f"(yr[u]), "f"(zr[u]),
@@ -495,14 +496,13 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     }
 }
 
-// launch shapes: 0 = 1024 threads x 2 points per lane, 1 = 768 x 2, 2 = 512 x 4 with the transform in registers
+// launch shapes: 0 = 1024 threads x 2 points per lane (config 7, the default), 1 = 512 x 4 with the transform in registers (config 8)
 using Shape0 = StreamShape<1024, 2, false>;
-using Shape1 = StreamShape<768, 2, false>;
-using Shape2 = StreamShape<512, 4, true>;
+using Shape1 = StreamShape<512, 4, true>;
 
-template <class C, bool FOV, bool FASTDIV>
+template <class C, bool FOV, bool FASTDIV, bool KEEPMASK>
 static int launch_one(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream) {
-    auto kern = stream_evidence_kernel<C, FOV, FASTDIV>;
+    auto kern = stream_evidence_kernel<C, FOV, FASTDIV, KEEPMASK>;
     MSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, args.L.total_bytes));
     kern<<<grid, C::kThreads, args.L.total_bytes, stream>>>(args, T, ws);
     MSC_CUDA(cudaGetLastError());
@@ -510,25 +510,21 @@ static int launch_one(const FusedArgs& args, const TableLayout& T, unsigned char
 }
 template <class C>
 static int launch_shape(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream) {
-    if (fov) return fast ? launch_one<C, true, true>(args, T, ws, grid, stream) : launch_one<C, true, false>(args, T, ws, grid, stream);
-    return fast ? launch_one<C, false, true>(args, T, ws, grid, stream) : launch_one<C, false, false>(args, T, ws, grid, stream);
+    if (fov && args.P.fov_keep_mask != 0u)
+        return fast ? launch_one<C, true, true, true>(args, T, ws, grid, stream) : launch_one<C, true, false, true>(args, T, ws, grid, stream);
+    if (fov) return fast ? launch_one<C, true, true, false>(args, T, ws, grid, stream) : launch_one<C, true, false, false>(args, T, ws, grid, stream);
+    return fast ? launch_one<C, false, true, false>(args, T, ws, grid, stream) : launch_one<C, false, false, false>(args, T, ws, grid, stream);
 }
 
 void stream_shape_info(int shape, int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes) {
-    switch (shape) {
-        case 1: *threads = Shape1::kThreads; *tile_pts = Shape1::kTilePts; *ring_bytes = Shape1::kRingBytes; *queue_bytes = Shape1::kQueueBytes; break;
-        case 2: *threads = Shape2::kThreads; *tile_pts = Shape2::kTilePts; *ring_bytes = Shape2::kRingBytes; *queue_bytes = Shape2::kQueueBytes; break;
-        default: *threads = Shape0::kThreads; *tile_pts = Shape0::kTilePts; *ring_bytes = Shape0::kRingBytes; *queue_bytes = Shape0::kQueueBytes; break;
-    }
+    if (shape == 1) { *threads = Shape1::kThreads; *tile_pts = Shape1::kTilePts; *ring_bytes = Shape1::kRingBytes; *queue_bytes = Shape1::kQueueBytes; }
+    else { *threads = Shape0::kThreads; *tile_pts = Shape0::kTilePts; *ring_bytes = Shape0::kRingBytes; *queue_bytes = Shape0::kQueueBytes; }
 }
 
 int launch_stream_kernel(int shape, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast,
                          cudaStream_t stream) {
-    switch (shape) {
-        case 1: return launch_shape<Shape1>(args, T, ws, grid, fov, fast, stream);
-        case 2: return launch_shape<Shape2>(args, T, ws, grid, fov, fast, stream);
-        default: return launch_shape<Shape0>(args, T, ws, grid, fov, fast, stream);
-    }
+    if (shape == 1) return launch_shape<Shape1>(args, T, ws, grid, fov, fast, stream);
+    return launch_shape<Shape0>(args, T, ws, grid, fov, fast, stream);
 }
 
 }  // namespace msc

@@ -100,7 +100,7 @@ def load():
     return lib
 
 
-DEFAULT_FUSED_CONFIG = 6  # launch shape the library selects by default (fused_evidence.cu: g_opt_config)
+DEFAULT_FUSED_CONFIG = 7  # launch shape the library selects by default (fused_evidence.cu: g_opt_config)
 
 
 def check(status: int, what: str):
