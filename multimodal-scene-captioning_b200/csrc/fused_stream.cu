@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                 uint32_t pass[PPT];
                 auto edge_test = [&](int u) {
                     const uint32_t sbits = st[u];
-                    const int e = __ffs((int)sbits) - 1;              // -1: nothing to test
                     const uint32_t low = sbits & (0u - sbits);        // lowest set bit (0 if none)
+                    const int e = 31 - __clz((int)low);               // its index; -1: nothing to test
                     st[u] = sbits ^ low;
                     const float4 E = lds128(edge_s + (uint32_t)(e * 16));
                     const float qx = __fsub_rn(xr[u], E.x), qy = __fsub_rn(yr[u], E.y);
@@ -413,8 +413,10 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                                  : "memory");
                 }
                 q_tail += __popc(m);
-                __syncwarp();
-                if (q_tail - q_head >= 32u) drain_queue(32u);
+                if (q_tail - q_head >= 32u) {
+                    __syncwarp();  // the entries stored above are visible to the lanes that test them
+                    drain_queue(32u);
+                }
             }
             ++wk;
             if (FOV) {
