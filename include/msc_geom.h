@@ -115,9 +115,17 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
 
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
  * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv",
- * "cull_shift" (-1 auto).  get: also "last_window", "last_smem", "tile_pts", "stages", "threads". */
+ * "cull_shift" (-1 auto), "config" (launch shape: 7 = second-generation kernel fused_stream.cu, the default; 8 = its 512-thread
+ * shape; 0-6 = first-generation kernel fused_evidence.cu), "time_kernel".  get: also "last_window", "last_smem", "tile_pts",
+ * "stages", "threads", "last_launches". */
 int msc_fused_set_option(const char* key, int32_t value);
 int msc_fused_get_option(const char* key, int32_t* value);
+
+/* Measurement aid (no reference counterpart): with option "time_kernel" = 1 every msc_fused_evidence_batch call brackets its
+ * streaming kernel -- not the small table kernels before it -- with CUDA events on the caller's stream (a ring of 64 pairs).
+ * Copies the durations in ms of the most recent n timed calls, oldest first, to out_ms_host after synchronising on their end
+ * events.  Returns the number written (<= n) or a negative msc_status.  get_option("last_launches") = kernels the last call launched. */
+int msc_fused_kernel_times(float* out_ms_host, int32_t n);
 
 /*
  * Materialised multi-sweep aggregation (devkit LidarPointCloud.from_file_multisweep, App. A.1) for one

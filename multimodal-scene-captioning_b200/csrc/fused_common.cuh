@@ -72,8 +72,10 @@ __device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, 
 // vectors) into the cull grid.  Every member point lies in the corner hull up to float rounding (<< the 2 mm
 // margin) and bev_cell() is monotonic, so a member can never fall in an unmarked cell.
 // cull_words: first id word of cell 0; STRIDE words between cells (2: the smem (ids, classes) pairs, 1: the workspace id table).
+// The cells of the box's bounding rectangle are dealt round-robin to `nworkers` callers (worker = 0 .. nworkers - 1).
 template <int STRIDE>
-static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint32_t* __restrict__ cull_words) {
+static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const float* __restrict__ o, int b, uint32_t* __restrict__ cull_words,
+                                                  int worker = 0, int nworkers = 1) {
     const msc_params& P = A.P;
     const FusedLayout& L = A.L;
     const float margin = 2e-3f;
@@ -88,8 +90,10 @@ static __device__ __noinline__ void rasterise_box(const FusedArgs& A, const floa
     const int cy1 = bev_cell<false>(cy + ry, P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1) >> L.cull_shift;
     const float cell_m = (A.two_r / A.resf) * (float)(1 << L.cull_shift);
     const int last = L.cull_dim - 1;
-    for (int gy = cy0; gy <= cy1; ++gy) {
-        for (int gx = cx0; gx <= cx1; ++gx) {
+    const int nx_cells = cx1 - cx0 + 1, n_cells = nx_cells * (cy1 - cy0 + 1);
+    for (int ci = worker; ci < n_cells; ci += nworkers) {
+        {
+            const int gy = cy0 + ci / nx_cells, gx = cx0 + ci % nx_cells;
             // edge cells absorb everything clipped into them: never reject those
             bool reject = false;
             if (gx > 0 && gx < last && gy > 0 && gy < last) {

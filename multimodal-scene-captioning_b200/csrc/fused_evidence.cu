@@ -214,10 +214,11 @@ __global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant
 }
 
 // Candidate-box ids per (sample, cull cell) for fused_stream.cu: the same conservative rasterisation the first-generation kernel
-// runs inside its per-sample prologue, one thread per box, into a workspace table the host pre-fills with kCullEmpty.
+// runs inside its per-sample prologue, one warp per box (lanes share the cells of its bounding rectangle), into a workspace table
+// the host pre-fills with kCullEmpty.
 __global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
                                                            unsigned char* __restrict__ ws) {
-    const int gb = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (gb >= n_boxes_total) return;
     int lo = 0, hi = A.in.n_samples;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.in.sample_box_off[mid] <= gb) lo = mid; else hi = mid; }
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constan
     if (b >= A.L.max_boxes) return;  // caller under-declared max_boxes_per_sample: the streaming kernel drops these boxes too
     const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)gb * kBoxStride;
     uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off) + (size_t)lo * (size_t)(A.L.cull_dim * A.L.cull_dim);
-    rasterise_box<1>(A, o, b, ids);
+    rasterise_box<1>(A, o, b, ids, lane, 32);
 }
 
 // ------------------------------------------------------------------------------------------------ streaming kernel
@@ -606,6 +607,27 @@ static int g_opt_debug_skip = 0;
 static int g_opt_config = 7;  // launch shape: 7 = second-generation kernel (fused_stream.cu), 1024 threads x 2 points per lane (default);
                               // 8 = the same kernel with 512 threads x 4 points per lane; first generation (this file): 0 = 512x2,4 ring
                               // stages; 1 = 512x2,3; 2 = 1024x2,2 pose in smem; 3 = 512x4,2; 4 = 768x2,3; 5 = 1024x1,4; 6 = shape 2 + candidate queue
+static int g_opt_time_kernel = 0;  // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
+static int g_last_launches = 0;    // kernels launched by the most recent msc_fused_evidence_batch call
+constexpr int kTimeRing = 64;
+static cudaEvent_t g_ev0[kTimeRing], g_ev1[kTimeRing];
+static bool g_ev_made = false;
+static long long g_ev_count = 0;  // calls timed so far
+static int time_begin(cudaStream_t stream) {
+    if (!g_opt_time_kernel) return MSC_OK;
+    if (!g_ev_made) {
+        for (int i = 0; i < kTimeRing; ++i) { MSC_CUDA(cudaEventCreate(&g_ev0[i])); MSC_CUDA(cudaEventCreate(&g_ev1[i])); }
+        g_ev_made = true;
+    }
+    MSC_CUDA(cudaEventRecord(g_ev0[g_ev_count % kTimeRing], stream));
+    return MSC_OK;
+}
+static int time_end(cudaStream_t stream) {
+    if (!g_opt_time_kernel) return MSC_OK;
+    MSC_CUDA(cudaEventRecord(g_ev1[g_ev_count % kTimeRing], stream));
+    ++g_ev_count;
+    return MSC_OK;
+}
 static int g_last_window = 0, g_last_smem = 0, g_last_fastdiv = 0, g_last_tile_pts = 0, g_last_stages = 0, g_last_threads = 0;
 
 // divisors 2*bev_range for which tools/markstein_check.c has been run over the full float range
@@ -681,14 +703,17 @@ static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned c
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
     if ((long long)args.in.n_samples * cams > work) work = (long long)args.in.n_samples * cams;
+    g_last_launches = 0;
     if (work > 0) {
         fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
         MSC_CUDA(cudaGetLastError());
+        ++g_last_launches;
     }
     if (fov) {
         const long long cells = (long long)args.in.n_samples * ncc;
         fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
+        ++g_last_launches;
     }
     return MSC_OK;
 }
@@ -703,10 +728,14 @@ static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* 
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
-    const int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
     if (rc != MSC_OK) return rc;
-    if (fov) return fast ? launch_fused<C, true, true>(args, T, ws, grid, stream) : launch_fused<C, true, false>(args, T, ws, grid, stream);
-    return fast ? launch_fused<C, false, true>(args, T, ws, grid, stream) : launch_fused<C, false, false>(args, T, ws, grid, stream);
+    if ((rc = time_begin(stream)) != MSC_OK) return rc;
+    if (fov) rc = fast ? launch_fused<C, true, true>(args, T, ws, grid, stream) : launch_fused<C, true, false>(args, T, ws, grid, stream);
+    else rc = fast ? launch_fused<C, false, true>(args, T, ws, grid, stream) : launch_fused<C, false, false>(args, T, ws, grid, stream);
+    if (rc != MSC_OK) return rc;
+    ++g_last_launches;
+    return time_end(stream);
 }
 
 // configs 7-8: the second-generation streaming kernel (fused_stream.cu), launch shapes 0-1
@@ -721,15 +750,19 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = tile_pts; g_last_stages = 2; g_last_threads = threads;
-    const int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
     if (rc != MSC_OK) return rc;
     const size_t ncc = (size_t)args.L.cull_dim * args.L.cull_dim;
     MSC_CUDA(cudaMemsetAsync(ws + T.cullids_off, 0xff, (size_t)args.in.n_samples * ncc * 4, stream));  // kCullEmpty
     if (n_boxes_total > 0) {
-        fused_cullids_kernel<<<(unsigned)((n_boxes_total + 127) / 128), 128, 0, stream>>>(args, T, n_boxes_total, ws);
+        fused_cullids_kernel<<<(unsigned)((n_boxes_total + 3) / 4), 128, 0, stream>>>(args, T, n_boxes_total, ws);
         MSC_CUDA(cudaGetLastError());
+        ++g_last_launches;
     }
-    return launch_stream_kernel(shape, args, T, ws, grid, fov, fast, stream);
+    if ((rc = time_begin(stream)) != MSC_OK) return rc;
+    if ((rc = launch_stream_kernel(shape, args, T, ws, grid, fov, fast, stream)) != MSC_OK) return rc;
+    ++g_last_launches;
+    return time_end(stream);
 }
 
 }  // namespace msc
@@ -749,6 +782,7 @@ int msc_fused_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "fastdiv")) { msc::g_opt_fastdiv = value ? 1 : 0; return MSC_OK; }
     if (!strcmp(key, "config")) { msc::g_opt_config = value; return MSC_OK; }
     if (!strcmp(key, "debug_skip")) { msc::g_opt_debug_skip = value; return MSC_OK; }
+    if (!strcmp(key, "time_kernel")) { msc::g_opt_time_kernel = value ? 1 : 0; return MSC_OK; }
     msc::set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
 }
@@ -766,8 +800,23 @@ int msc_fused_get_option(const char* key, int32_t* value) {
     if (!strcmp(key, "tile_pts")) { *value = msc::g_last_tile_pts; return MSC_OK; }
     if (!strcmp(key, "stages")) { *value = msc::g_last_stages; return MSC_OK; }
     if (!strcmp(key, "threads")) { *value = msc::g_last_threads; return MSC_OK; }
+    if (!strcmp(key, "last_launches")) { *value = msc::g_last_launches; return MSC_OK; }
+    if (!strcmp(key, "time_kernel")) { *value = msc::g_opt_time_kernel; return MSC_OK; }
     msc::set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
+}
+
+int msc_fused_kernel_times(float* out_ms_host, int32_t n) {
+    using namespace msc;
+    MSC_REQUIRE(out_ms_host && n >= 0, "bad argument");
+    const long long have = g_ev_count < kTimeRing ? g_ev_count : kTimeRing;
+    const int take = (int)(n < have ? n : have);
+    for (int i = 0; i < take; ++i) {
+        const long long k = g_ev_count - take + i;
+        MSC_CUDA(cudaEventSynchronize(g_ev1[k % kTimeRing]));
+        MSC_CUDA(cudaEventElapsedTime(out_ms_host + i, g_ev0[k % kTimeRing], g_ev1[k % kTimeRing]));
+    }
+    return take;
 }
 
 int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, const msc_batch_out* out, void* workspace,

@@ -53,6 +53,7 @@ _PROTOS = {
                                            C.c_size_t, C.c_void_p]),
     "msc_fused_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "msc_fused_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
+    "msc_fused_kernel_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32]),
     "msc_aggregate_sweeps": (C.c_int, [C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "msc_keyframe_filter_split": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -117,3 +118,12 @@ def get_option(key: str) -> int:
     v = C.c_int32(0)
     check(load().msc_fused_get_option(key.encode(), C.byref(v)), f"get_option({key})")
     return int(v.value)
+
+
+def kernel_times(n: int = 64):
+    """Durations (ms) of the streaming kernel in the most recent calls timed with set_option("time_kernel", 1), oldest first."""
+    buf = (C.c_float * max(n, 1))()
+    got = load().msc_fused_kernel_times(buf, int(n))
+    if got < 0:
+        check(got, "msc_fused_kernel_times")
+    return [float(buf[i]) for i in range(got)]

@@ -172,7 +172,7 @@ class GeometryEngine:
             ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
         _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
                                                       C.c_void_p(stream)), "msc_fused_evidence_batch")
-        self.kernel_launches += 3 if _capi.get_option("fov") else 2  # tables (+ wedge classes) + streaming kernel
+        self.kernel_launches += _capi.get_option("last_launches")  # table kernels + the streaming kernel, counted by the library
         return out
 
     # ------------------------------------------------------------------ batched pairwise relation tables ([EXT] e6)
