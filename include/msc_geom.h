@@ -116,7 +116,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
  * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv",
  * "cull_shift" (-1 auto), "config" (launch shape: 7 = second-generation kernel fused_stream.cu, the default; 8 = its 512-thread
- * shape; 0-6 = first-generation kernel fused_evidence.cu), "time_kernel".  get: also "last_window", "last_smem", "tile_pts",
+ * shape; 6 and 0 = two shapes of the first-generation kernel fused_evidence.cu), "time_kernel".  get: also "last_window", "last_smem", "tile_pts",
  * "stages", "threads", "last_launches". */
 int msc_fused_set_option(const char* key, int32_t value);
 int msc_fused_get_option(const char* key, int32_t* value);

@@ -1,5 +1,5 @@
 // fused_common.cuh -- types and device helpers shared by the two generations of the streaming kernel
-// (fused_evidence.cu: configs 0-6; fused_stream.cu: config 7, the default).
+// (fused_evidence.cu: configs 0 and 6; fused_stream.cu: configs 7, the default, and 8).
 #pragma once
 #include "msc_common.cuh"
 
@@ -54,7 +54,7 @@ struct TableLayout {  // offsets (bytes) into the workspace
     size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, cullids_off, total;
 };
 
-// fused_stream.cu (configs 7-9): bytes of its per-CTA state block, and its launcher
+// fused_stream.cu (configs 7-8): bytes of its per-CTA state block, and its launcher
 int stream_misc_bytes();
 void stream_shape_info(int shape, int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
 int launch_stream_kernel(int shape, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast,

@@ -605,8 +605,8 @@ static int g_opt_cull_shift = -1;  // -1 = auto (cull cell ~ 2 m)
 static int g_opt_fastdiv = 1;      // allow the Markstein division for whitelisted divisors
 static int g_opt_debug_skip = 0;
 static int g_opt_config = 7;  // launch shape: 7 = second-generation kernel (fused_stream.cu), 1024 threads x 2 points per lane (default);
-                              // 8 = the same kernel with 512 threads x 4 points per lane; first generation (this file): 0 = 512x2,4 ring
-                              // stages; 1 = 512x2,3; 2 = 1024x2,2 pose in smem; 3 = 512x4,2; 4 = 768x2,3; 5 = 1024x1,4; 6 = shape 2 + candidate queue
+                              // 8 = the same kernel with 512 threads x 4 points per lane; first generation (this file): 6 = 1024 x 2, pose
+                              // rows in smem, candidate queue (its final shape); any other value = 512 x 2, four ring stages, pose in registers
 static int g_opt_time_kernel = 0;  // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
 static int g_last_launches = 0;    // kernels launched by the most recent msc_fused_evidence_batch call
 constexpr int kTimeRing = 64;
@@ -861,12 +861,7 @@ int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, c
     const int grid = in->n_samples < sms ? in->n_samples : sms;
     switch (g_opt_config) {
         case 7: case 8: return dispatch_stream(g_opt_config - 7, args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
-        case 1: return dispatch_fused<Cfg<512, 2, 3>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
-        case 2: return dispatch_fused<Cfg<1024, 2, 2, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
-        case 3: return dispatch_fused<Cfg<512, 4, 2>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         case 6: return dispatch_fused<Cfg<1024, 2, 2, true, 1>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
-        case 4: return dispatch_fused<Cfg<768, 2, 3, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
-        case 5: return dispatch_fused<Cfg<1024, 1, 4, true>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
         default: return dispatch_fused<Cfg<512, 2, 4>>(args, T, ws, in->n_boxes, smem_optin, grid, fov, fast, stream);
     }
 }

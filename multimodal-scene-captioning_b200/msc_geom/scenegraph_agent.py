@@ -12,7 +12,7 @@ from typing import Any, Dict, List, Optional
 
 import numpy as np
 
-from . import ops
+from . import ops, serialize
 from .engine import GeometryEngine
 from .layout import boxes_from_annotations
 
@@ -105,6 +105,12 @@ class SceneGraphAgent:
         rel = ops.relation_table(self.engine, boxes_from_annotations(annotations), None if ego_pose is None else np.asarray(ego_pose, np.float64))
         rel["labels"] = ("ahead", "left", "behind", "right")
         return rel
+
+    def scene_graph_prompt(self, annotations: List[Dict], context: Optional[Dict] = None) -> str:
+        """The user message the reference sends to its LLM in _generate_scene_graph (scenegraph_agent.py:327-366), built from the
+        GPU-computed annotation table; equal to the reference's string (tests/test_serialize.py)."""
+        objs = self._parse_annotations(annotations)
+        return serialize.scene_graph_user_prompt(self._categorize_objects(objs), self._build_spatial_zones(objs), annotations, context)
 
     def process(self, annotations: List[Dict], context: Optional[Dict] = None) -> Dict[str, Any]:
         objs = self._parse_annotations(annotations)
