@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
 }
 
 // wedge classes per (sample, cull cell), from the wedges the table kernel wrote (launched after it on the same stream)
-__global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
+// per_edge = false: wedge classes (u16) for the first-generation kernel; true: edge classes (u32) for fused_stream.cu
+__global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws,
+                                                          bool per_edge) {
     const msc_params& P = A.P;
     const int n_cams = P.n_cams;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,29 +205,33 @@ __global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant
     const float y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad);
     const float y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
     uint32_t bits = 0, ebits = 0;
-    for (int c = 0; c < n_cams; ++c) {
-        const uint32_t k = classify_cell(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
-        bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
-        const uint32_t e = classify_cell_edges(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
-        ebits |= ((e & 1u) << c) | (((e >> 1) & 1u) << (8 + c)) | (((e >> 2) & 1u) << (16 + c));  // in-bit, right / left edge undecided
+    if (per_edge) {
+        for (int c = 0; c < n_cams; ++c) {
+            const uint32_t e = classify_cell_edges(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
+            ebits |= ((e & 1u) << c) | (((e >> 1) & 1u) << (8 + c)) | (((e >> 2) & 1u) << (16 + c));  // in-bit, right / left edge undecided
+        }
+        reinterpret_cast<uint32_t*>(ws + T.edgecls_off)[(size_t)sample * ncc + i] = ebits;
+    } else {
+        for (int c = 0; c < n_cams; ++c) {
+            const uint32_t k = classify_cell(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, x0, x1, y0, y1);
+            bits |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c));
+        }
+        fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
     }
-    fovcls[(size_t)sample * ncc + i] = (uint16_t)bits;
-    reinterpret_cast<uint32_t*>(ws + T.edgecls_off)[(size_t)sample * ncc + i] = ebits;
 }
 
 // Candidate-box ids per (sample, cull cell) for fused_stream.cu: the same conservative rasterisation the first-generation kernel
 // runs inside its per-sample prologue, one warp per box (lanes share the cells of its bounding rectangle), into a workspace table
 // the host pre-fills with kCullEmpty.
-__global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
-                                                           unsigned char* __restrict__ ws) {
-    const int gb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (gb >= n_boxes_total) return;
-    int lo = 0, hi = A.in.n_samples;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.in.sample_box_off[mid] <= gb) lo = mid; else hi = mid; }
-    const int b = gb - A.in.sample_box_off[lo];
-    if (b >= A.L.max_boxes) return;  // caller under-declared max_boxes_per_sample: the streaming kernel drops these boxes too
-    const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)gb * kBoxStride;
-    uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off) + (size_t)lo * (size_t)(A.L.cull_dim * A.L.cull_dim);
+__global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
+    const int sample = blockIdx.x, lane = threadIdx.x & 31;
+    const int b = (blockIdx.y * blockDim.x + threadIdx.x) >> 5;  // box of this warp inside its sample
+    const int bx0 = A.in.sample_box_off[sample];
+    int n_boxes = A.in.sample_box_off[sample + 1] - bx0;
+    if (n_boxes > A.L.max_boxes) n_boxes = A.L.max_boxes;  // caller under-declared max_boxes_per_sample: the streaming kernel drops these boxes too
+    if (b >= n_boxes) return;
+    const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)(bx0 + b) * kBoxStride;
+    uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off) + (size_t)sample * (size_t)(A.L.cull_dim * A.L.cull_dim);
     rasterise_box<1>(A, o, b, ids, lane, 32);
 }
 
@@ -698,7 +704,8 @@ static int launch_fused(const FusedArgs& args, const TableLayout& T, unsigned ch
     return MSC_OK;
 }
 // tables (prepared boxes, projection, wedges, wedge classes -> workspace), launched before either streaming kernel
-static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, bool fov, cudaStream_t stream) {
+static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, bool fov, bool per_edge,
+                         cudaStream_t stream) {
     const int ncc = args.L.cull_dim * args.L.cull_dim;
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
@@ -711,7 +718,7 @@ static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned c
     }
     if (fov) {
         const long long cells = (long long)args.in.n_samples * ncc;
-        fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws);
+        fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws, per_edge);
         MSC_CUDA(cudaGetLastError());
         ++g_last_launches;
     }
@@ -728,7 +735,7 @@ static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* 
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = C::kTilePts; g_last_stages = C::kStages; g_last_threads = C::kThreads;
-    int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    int rc = launch_tables(args, T, ws, n_boxes_total, fov, false, stream);
     if (rc != MSC_OK) return rc;
     if ((rc = time_begin(stream)) != MSC_OK) return rc;
     if (fov) rc = fast ? launch_fused<C, true, true>(args, T, ws, grid, stream) : launch_fused<C, true, false>(args, T, ws, grid, stream);
@@ -750,12 +757,13 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = tile_pts; g_last_stages = 2; g_last_threads = threads;
-    int rc = launch_tables(args, T, ws, n_boxes_total, fov, stream);
+    int rc = launch_tables(args, T, ws, n_boxes_total, fov, true, stream);
     if (rc != MSC_OK) return rc;
     const size_t ncc = (size_t)args.L.cull_dim * args.L.cull_dim;
     MSC_CUDA(cudaMemsetAsync(ws + T.cullids_off, 0xff, (size_t)args.in.n_samples * ncc * 4, stream));  // kCullEmpty
-    if (n_boxes_total > 0) {
-        fused_cullids_kernel<<<(unsigned)((n_boxes_total + 3) / 4), 128, 0, stream>>>(args, T, n_boxes_total, ws);
+    if (n_boxes_total > 0 && args.L.max_boxes > 0) {
+        const dim3 cgrid((unsigned)args.in.n_samples, (unsigned)((args.L.max_boxes + 3) / 4));  // a warp per box, one grid column per sample
+        fused_cullids_kernel<<<cgrid, 128, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
         ++g_last_launches;
     }
