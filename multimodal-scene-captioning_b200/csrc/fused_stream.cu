@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     const bool close = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
                     keep[u] = valid & !close;
                     xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
-                    c_close += keep[u] ? 1u : 0u;
+                    if (keep[u]) ++c_close;
                 }
                 __syncwarp();  // every lane has read its rows: the slot may be refilled at the top of the next iteration
                 // A.1 f64 matrix x f32 point -> f32, one matrix row at a time
@@ -377,11 +377,10 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     cam_hi += ((in_bits[u] >> 4) * 0x00204081u) & 0x01010101u;
                     if (KEEPMASK && (in_bits[u] & P.fov_keep_mask) == 0u) keep[u] = false;  // fov_keep_mask != 0: a FOV filter, not only counts
                 }
-                c_kept += keep[u] ? 1u : 0u;
-                c_ground += (keep[u] && zr[u] < P.ground_z) ? 1u : 0u;  // lidar_agent.py:128
+                if (keep[u]) ++c_kept;
+                if (keep[u] && zr[u] < P.ground_z) ++c_ground;  // lidar_agent.py:128
                 // Q8 intensity, clamp [0, 65535]; NaN -> 0
-                const float qf = fminf(fmaxf(__fmul_rn(inten[u], A.iscale), 0.0f), 65535.0f);
-                q[u] = (uint32_t)__float2int_rn(qf);
+                q[u] = min(__float2uint_rn(__fmul_rn(inten[u], A.iscale)), 65535u);  // the conversion saturates at 0 and maps NaN to 0
                 const bool to_window = keep[u] && wc_s[u] != 0u;
                 const uint32_t wa = to_window ? wc_s[u] : sink_s;
                 red_shared_add(wa, 1u);
