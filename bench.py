@@ -334,9 +334,9 @@ def main():
                 "call_ms": call_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
     cpu = None
     if not args.no_cpu and world == 1:
-        n_cpu = args.cpu_samples or 4 * cores
+        n_cpu = args.cpu_samples or 16 * cores  # ~2 s wall on 16 threads = ~30 s of CPU work on the bounded sample
         v, dt = cpu_oracle_throughput(hb_u, params, n_cpu, cores)
-        v1, _ = cpu_oracle_throughput(hb_u, params, 4, 1)
+        v1, _ = cpu_oracle_throughput(hb_u, params, 8, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": v1,
                "sample": f"{n_cpu} samples of the same workload, scalar C oracle (oracle/c/msc_oracle.c), {cores} threads, {dt:.1f} s wall"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
