@@ -88,6 +88,32 @@ def test_fused_crowded_cell_and_max_boxes(engine):
     check_fused(engine, [big])
 
 
+def test_fused_under_declared_max_boxes_sets_the_flag(engine):
+    """A caller that under-declares max_boxes_per_sample: the first max_boxes boxes are exact, the overflow bit of stats[13] is set,
+    everything that does not depend on boxes is unaffected -- in both kernel generations."""
+    import dataclasses
+    import torch
+    s = [make_sample(45, n_sweeps=2, n_boxes=12), make_sample(46, n_sweeps=1, n_boxes=4)]
+    hb = pack_batch(s)
+    p = GeomParams()
+    cut = dataclasses.replace(hb, max_boxes_per_sample=5)
+    for cfg in (6, 7):
+        _capi.set_option("config", cfg)
+        out = engine.run_fused(engine.upload(cut), params=p); torch.cuda.synchronize()
+        got = out.to_host()
+        for i in range(2):
+            ref = OB.oracle_fused(hb, i, p)
+            b0 = hb.sample_box_off[i]
+            n_ok = min(5, hb.sample_box_off[i + 1] - b0)
+            for k in ("box_count", "box_nearest", "box_centroid"):
+                assert np.array_equal(got[k][b0:b0 + n_ok], ref[k][:n_ok]), (cfg, i, k)
+            for k in ("proj_visible", "proj_extent"):
+                assert np.array_equal(got[k][b0:hb.sample_box_off[i + 1]], ref[k]), (cfg, i, k)
+            assert np.array_equal(got["bev_count"][i], ref["bev_count"]) and np.array_equal(got["stats"][i][:13], ref["stats"][:13])
+            assert bool(got["stats"][i][13] >> 31) == (i == 0), (cfg, i, got["stats"][i][13])
+    _capi.set_option("config", _capi.DEFAULT_FUSED_CONFIG)
+
+
 def test_fused_fov_filter_and_weird_values(engine):
     s = make_sample(50, n_sweeps=3, n_boxes=30)
     raw = s["lidar_sweeps"][1]["points_raw"]
