@@ -1,15 +1,19 @@
-// fused_stream.cu -- second generation of the streaming kernel (launch shape "config" 7, the default).
+// fused_stream.cu -- second generation of the streaming kernel (launch shapes "config" 7, the default, and 8).
 //
 // Same arithmetic, per point, as fused_evidence.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); what
 // changed is the control structure, because the first generation was instruction-issue bound (ncu: 80 % of issue
 // slots, 353 warp instructions per 32 points, 20 of 32 lanes active):
-//   * the per-point phase after the transform is straight-line code with predicated atomics instead of a divergent
-//     `if (kept)` region per point with nested branches for window / periphery / height;
+//   * the per-point phase after the transform is straight-line code: dropped / out-of-window points add into a per-lane
+//     sink word instead of branching around the window atomics, and the rare periphery / max-height reductions share
+//     one region whose base pointers are read back from smem;
 //   * camera wedges are classified per EDGE and per cull cell: a point in a cell that straddles one image-column
-//     ray evaluates that one cross product (one LDS.128), not both edges of the wedge from six scalar loads;
+//     ray evaluates that one cross product (one LDS.128), not both edges of the wedge from six scalar loads; the test
+//     is branch-free, two rounds are peeled for all lanes and a loop takes the few points that need more;
 //   * one tile cursor (the tile in flight) instead of separate producer / consumer cursors, 32-bit shared addresses
-//     computed once, the warp index made warp-uniform for the compiler;
-//   * crowded cull cells ("test every box") go through the candidate queue like every other candidate.
+//     from one opaque base register, the warp index made warp-uniform for the compiler;
+//   * candidate-box ids per cull cell come from a pre-kernel (fused_evidence.cu: fused_cullids_kernel), so the
+//     per-sample prologue only copies tables; crowded cells ("test every box") go through the candidate queue.
+// 555 warp instructions per 64-point warp tile instead of 706 (profiles/r1b_stream_evidence_ncu_full.txt).
 #include "fused_common.cuh"
 
 namespace msc {
