@@ -216,13 +216,19 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                 const uint32_t fx = (uint32_t)(__float2int_rn(__fmul_rn(e.x, A.cscale)) + A.centroid_bias);
                 const uint32_t fy = (uint32_t)(__float2int_rn(__fmul_rn(e.y, A.cscale)) + A.centroid_bias);
                 const uint32_t fz = (uint32_t)(__float2int_rn(__fmul_rn(e.z, A.cscale)) + A.centroid_bias);
+                // centroid sums: one 32-bit word per axis plus a carry word that takes a rare second atomic when the word wraps
+                // (the coordinate is a 24-bit value, so that is at most once per 256 points); still order-independent integers
                 auto accumulate = [&](int b) {
                     const uint32_t acc_s = smem_s + (uint32_t)L.boxacc_off + (uint32_t)b * (uint32_t)(kAccWords * 4);
                     red_shared_add(acc_s, 1u);
                     asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(acc_s + 4u), "r"(__float_as_uint(es2)) : "memory");
-                    red_shared_add(acc_s + 8u, fx & 4095u); red_shared_add(acc_s + 12u, fx >> 12);
-                    red_shared_add(acc_s + 16u, fy & 4095u); red_shared_add(acc_s + 20u, fy >> 12);
-                    red_shared_add(acc_s + 24u, fz & 4095u); red_shared_add(acc_s + 28u, fz >> 12);
+                    uint32_t ox, oy, oz;
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(ox) : "r"(acc_s + 8u), "r"(fx) : "memory");
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(oy) : "r"(acc_s + 12u), "r"(fy) : "memory");
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(oz) : "r"(acc_s + 16u), "r"(fz) : "memory");
+                    if (ox > ~fx) red_shared_add(acc_s + 20u, 1u);
+                    if (oy > ~fy) red_shared_add(acc_s + 24u, 1u);
+                    if (oz > ~fz) red_shared_add(acc_s + 28u, 1u);
                 };
                 int hit = -1;
                 if (ids == kCullAll) {  // crowded cell (more than four boxes): test every box
@@ -469,7 +475,6 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                 const uint32_t cnt = acc[0];
                 const size_t o = (size_t)(bx0 + b);
                 A.out.box_count[o] = cnt;
-                if (cnt >= (1u << 20)) flags |= 2u;  // 12-bit limb sums may have wrapped
                 if (cnt == 0) {
                     A.out.box_nearest[o] = INFINITY;
                     A.out.box_centroid[o * 3 + 0] = 0.0f; A.out.box_centroid[o * 3 + 1] = 0.0f; A.out.box_centroid[o * 3 + 2] = 0.0f;
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     const double den = (double)cnt * (double)A.cscale;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const unsigned long long biased = (unsigned long long)acc[2 + 2 * k] + ((unsigned long long)acc[3 + 2 * k] << 12);
+                        const unsigned long long biased = (unsigned long long)acc[2 + k] + ((unsigned long long)acc[5 + k] << 32);
                         const long long sum = (long long)biased - (long long)cnt * (long long)A.centroid_bias;
                         A.out.box_centroid[o * 3 + k] = (float)((double)sum / den);
                     }
