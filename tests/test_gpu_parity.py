@@ -71,6 +71,8 @@ def test_fused_ragged_and_empty_inputs(engine):
     d = {"point_cloud": np.random.default_rng(5).normal(0, 12, (5000, 4)).astype(np.float32), "annotations": []}  # plain reference-style sample
     for cfg in (0, 6, 7, 8):
         check_fused(engine, [a, b, c, d], config=cfg)
+    check_fused(engine, [d])                    # a batch without a single box
+    check_fused(engine, [c])                    # ... and one without a single point
 
 
 def test_fused_crowded_cell_and_max_boxes(engine):
