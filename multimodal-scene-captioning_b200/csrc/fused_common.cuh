@@ -13,11 +13,13 @@ constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the 
 constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs; the odd
                                               // stride spreads the same word of different boxes over all 32 banks
 constexpr int kMaxWarps = 32;
+constexpr int kInnerMax = 50;  // fused_stream.cu: side of the fine (one BEV cell) edge-class grid around the sensor
 
 struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
     int32_t tiles_off, window_off, cull_off, boxp_off, boxacc_off, misc_off, queue_off, total_bytes;
     int32_t win_w, win_lo;         // window covers cells [win_lo, win_lo + win_w) in x and y
     int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
+    int32_t inner_off, inner_dim, inner_lo;  // fused_stream.cu: edge classes per BEV cell for cells [inner_lo, inner_lo + inner_dim)^2 (0: none)
     int32_t max_boxes;             // capacity of the smem box tables
 };
 
@@ -51,7 +53,7 @@ __device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp
 }
 
 struct TableLayout {  // offsets (bytes) into the workspace
-    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, cullids_off, total;
+    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, innercls_off, cullids_off, total;
 };
 
 // fused_stream.cu (configs 7-8): bytes of its per-CTA state block, and its launcher

@@ -193,12 +193,28 @@ __global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant
     const float* const wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
     uint16_t* const fovcls = reinterpret_cast<uint16_t*>(ws + T.fovcls_off);
     const int ncc = A.L.cull_dim * A.L.cull_dim;
-    if (gid >= A.in.n_samples * ncc) return;
-    const int sample = gid / ncc, i = gid - sample * ncc;
+    const int n_inner = per_edge ? A.L.inner_dim * A.L.inner_dim : 0;  // fine cells around the sensor (fused_stream.cu only)
+    const int per_sample = ncc + n_inner;
+    if (gid >= A.in.n_samples * per_sample) return;
+    const int sample = gid / per_sample, i = gid - sample * per_sample;
+    const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
+    if (i >= ncc) {  // one BEV cell: every point whose bev_cell() index is (ix, iy) lies in the padded square
+        const int j = i - ncc, jy = j / A.L.inner_dim, jx = j - jy * A.L.inner_dim;
+        const float cell_b = A.two_r / A.resf;
+        const int ix = A.L.inner_lo + jx, iy = A.L.inner_lo + jy, last_b = P.bev_res - 1;  // first / last BEV cells absorb what is clipped into them
+        const float fx0 = (ix == 0) ? -big : (-P.bev_range + (float)ix * cell_b - pad), fx1 = (ix == last_b) ? big : (-P.bev_range + (float)(ix + 1) * cell_b + pad);
+        const float fy0 = (iy == 0) ? -big : (-P.bev_range + (float)iy * cell_b - pad), fy1 = (iy == last_b) ? big : (-P.bev_range + (float)(iy + 1) * cell_b + pad);
+        uint32_t eb = 0;
+        for (int c = 0; c < n_cams; ++c) {
+            const uint32_t k = classify_cell_edges(wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6, fx0, fx1, fy0, fy1);
+            eb |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c)) | (((k >> 2) & 1u) << (16 + c));
+        }
+        reinterpret_cast<uint32_t*>(ws + T.innercls_off)[(size_t)sample * n_inner + j] = eb;
+        return;
+    }
     const int gy = i / A.L.cull_dim, gx = i - gy * A.L.cull_dim;
     const float cell_m = (A.two_r / A.resf) * (float)(1 << A.L.cull_shift);
     const int last = A.L.cull_dim - 1;
-    const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
     // edge cells absorb everything clipped into them
     const float x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad);
     const float x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
@@ -665,12 +681,14 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes)
     T.wedge_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * MSC_MAX_CAMS * 6 * 4);
     T.fovcls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 2);
     T.edgecls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 4);
+    T.innercls_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * kInnerMax * kInnerMax * 4);
     T.cullids_off = off; off = align(off + (size_t)(n_samples > 0 ? n_samples : 1) * dim * dim * 4);
     T.total = off;
     return T;
 }
 
-static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, int queue_bytes, int misc_bytes, FusedLayout* L) {
+static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_limit, int ring_bytes, int queue_bytes, int misc_bytes, int inner_dim,
+                          FusedLayout* L) {
     const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
     cull_geometry(P, &L->cull_shift, &L->cull_dim);
     L->max_boxes = cap;
@@ -681,6 +699,8 @@ static int compute_layout(const msc_params& P, int max_boxes_in_batch, int smem_
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
     L->misc_off = off; off += (misc_bytes + 127) & ~127;
+    L->inner_dim = inner_dim; L->inner_lo = (P.bev_res - inner_dim) / 2;
+    L->inner_off = off; off += (inner_dim * inner_dim * 4 + 127) & ~127;
     L->window_off = off;
     const int avail = smem_limit - off;
     if (avail < 0) return -1;
@@ -717,7 +737,7 @@ static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned c
         ++g_last_launches;
     }
     if (fov) {
-        const long long cells = (long long)args.in.n_samples * ncc;
+        const long long cells = (long long)args.in.n_samples * (ncc + (per_edge ? args.L.inner_dim * args.L.inner_dim : 0));
         fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws, per_edge);
         MSC_CUDA(cudaGetLastError());
         ++g_last_launches;
@@ -728,7 +748,7 @@ static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned c
 template <class C>
 static int dispatch_fused(FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int smem_optin, int grid, bool fov,
                           bool fast, cudaStream_t stream) {
-    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, C::kQueueBytes, (int)sizeof(Misc), &args.L) != 0) {
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, C::kRingBytes, C::kQueueBytes, (int)sizeof(Misc), 0, &args.L) != 0) {
         set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
         return MSC_ERR_UNSUPPORTED;
     }
@@ -750,7 +770,10 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
                            bool fov, bool fast, cudaStream_t stream) {
     int threads = 0, tile_pts = 0, ring = 0, queue = 0;
     stream_shape_info(shape, &threads, &tile_pts, &ring, &queue);
-    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, ring, queue, stream_misc_bytes(), &args.L) != 0) {
+    // fine edge classes for the kInnerMax x kInnerMax BEV cells around the sensor, where several image-column rays cross a 2 m cull cell
+    int inner = fov ? (args.P.bev_res < kInnerMax ? args.P.bev_res : kInnerMax) : 0;
+    inner &= ~1;
+    if (compute_layout(args.P, args.in.max_boxes_per_sample, smem_optin, ring, queue, stream_misc_bytes(), inner, &args.L) != 0) {
         set_error("shared-memory layout does not fit (%d bytes available)", smem_optin);
         return MSC_ERR_UNSUPPORTED;
     }

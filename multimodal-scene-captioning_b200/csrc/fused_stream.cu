@@ -18,7 +18,7 @@
 
 namespace msc {
 
-constexpr int kStreamPoseSmem = 32;  // sweeps whose transforms are staged per sample; later ones use a per-warp slot
+constexpr int kStreamPoseSmem = 12;  // sweeps whose transforms are staged per sample; later ones use a per-warp slot
 
 // Launch shape: NT threads = NT/32 warps; every warp owns two ring slots of 32*PPT points and a 64-entry candidate queue.
 // POSE_REG keeps the current sweep's 3x4 f64 transform in registers (shapes with a 128-register budget).
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     const float* const g_wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
     const uint32_t* const g_edgecls = reinterpret_cast<const uint32_t*>(ws + T.edgecls_off);
     const uint32_t* const g_cullids = reinterpret_cast<const uint32_t*>(ws + T.cullids_off);
+    const uint32_t* const g_innercls = reinterpret_cast<const uint32_t*>(ws + T.innercls_off);
 
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform as far as the compiler is concerned
@@ -176,6 +177,11 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
             const uint32_t* ec = g_edgecls + (size_t)sample * n_cull;
             const uint32_t* ids = g_cullids + (size_t)sample * n_cull;  // candidate boxes per cull cell (fused_cullids_kernel)
             for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(ids[i], (FOV && n_cams > 0) ? ec[i] : 0u);
+            if (FOV) {  // fine edge classes of the BEV cells around the sensor
+                const int n_inner = L.inner_dim * L.inner_dim;
+                uint32_t* inner = reinterpret_cast<uint32_t*>(smem + L.inner_off);
+                for (int i = tid; i < n_inner; i += NT) inner[i] = g_innercls[(size_t)sample * n_inner + i];
+            }
             for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
             const float4* bsrc = reinterpret_cast<const float4*>(g_boxprep + (size_t)bx0 * kBoxStride);
             for (int i = tid; i < n_boxes * (kBoxStride / 4); i += NT) reinterpret_cast<float4*>(boxp)[i] = bsrc[i];
@@ -331,17 +337,28 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                 // BEV cell, lidar_agent.py:547-552 (garbage for dropped points is clamped and never used)
                 const int ix = bev_cell<FASTDIV>(xr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
                 const int iy = bev_cell<FASTDIV>(yr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, res_m1);
-                const uint2 ce = cull[(iy >> L.cull_shift) * L.cull_dim + (ix >> L.cull_shift)];
-                cand[u] = ce.x;
-                in_bits[u] = ce.y & 0xffu;
-                st[u] = (FOV && keep[u]) ? (ce.y >> 8) : 0u;  // bit c: right edge of camera c undecided in this cell, bit 8 + c: left edge
+                const uint32_t ce_s = smem_s + (uint32_t)L.cull_off + (uint32_t)(((iy >> L.cull_shift) * L.cull_dim + (ix >> L.cull_shift)) << 3);
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cand[u]) : "r"(ce_s));
+                if (FOV) {
+                    // edge classes: from the fine grid (one BEV cell) around the sensor, where a 2 m cull cell is crossed by several
+                    // image-column rays, else from the cull cell; one load either way
+                    const uint32_t jx = (uint32_t)(ix - L.inner_lo), jy = (uint32_t)(iy - L.inner_lo);
+                    const bool fine = jx < (uint32_t)L.inner_dim && jy < (uint32_t)L.inner_dim;
+                    const uint32_t cls_s = fine ? smem_s + (uint32_t)L.inner_off + ((jy * (uint32_t)L.inner_dim + jx) << 2) : ce_s + 4u;
+                    uint32_t cls;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cls) : "r"(cls_s));
+                    in_bits[u] = cls & 0xffu;
+                    st[u] = keep[u] ? (cls >> 8) : 0u;  // bit c: right edge of camera c undecided in this cell, bit 8 + c: left edge
+                } else {
+                    in_bits[u] = 0u; st[u] = 0u;
+                }
                 cell[u] = (uint32_t)iy * (uint32_t)res + (uint32_t)ix;
                 const uint32_t wx = (uint32_t)(ix - L.win_lo), wy = (uint32_t)(iy - L.win_lo);
                 const bool inwin = wx < (uint32_t)L.win_w && wy < (uint32_t)L.win_w;
                 wc_s[u] = inwin ? window_s + ((wy * (uint32_t)L.win_w + wx) << 3) : 0u;  // 0: periphery, one 64-bit global RED
             }
             // ---- phase B: one exact cross product per image-column ray a point's cull cell straddles.  The test is branch-free
-            // (a point with nothing left to test reads the table entry before edge[0] and clears no bit); two rounds cover
+            // (a point with nothing left to test reads the table entry before edge[0] and clears no bit); one round covers
             // nearly every point, a loop takes the rest.
             if (FOV) {
                 uint32_t pass[PPT];
@@ -360,10 +377,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) pass[u] = 0xffffu;
 #pragma unroll
-                for (int round = 0; round < 2; ++round) {
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u) edge_test(u);
-                }
+                for (int u = 0; u < PPT; ++u) edge_test(u);  // one round for every lane; with the fine grid a second ray is rare
                 uint32_t left_over = 0;
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) left_over |= st[u];
