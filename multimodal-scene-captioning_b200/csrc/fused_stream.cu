@@ -13,7 +13,7 @@
 //     from one opaque base register, the warp index made warp-uniform for the compiler;
 //   * candidate-box ids per cull cell come from a pre-kernel (fused_evidence.cu: fused_cullids_kernel), so the
 //     per-sample prologue only copies tables; crowded cells ("test every box") go through the candidate queue.
-// 555 warp instructions per 64-point warp tile instead of 706 (profiles/r1b_stream_evidence_ncu_full.txt).
+// 530 warp instructions per 64-point warp tile instead of 706 (profiles/r1b_stream_evidence_ncu_full.txt).
 #include "fused_common.cuh"
 
 namespace msc {
