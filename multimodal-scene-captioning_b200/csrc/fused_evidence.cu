@@ -86,20 +86,18 @@ __device__ __forceinline__ uint32_t classify_cell(const float* __restrict__ wq, 
 }
 
 // Per-edge classes of one cull cell against one wedge (fused_stream.cu): bit0 = the wedge may contain points of the cell,
-// bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same corner extremes and guard band as
-// classify_cell(); an edge every point of the cell passes needs no exact test, an edge every point fails empties the wedge.
+// bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same extremes over the cell and the same guard band
+// as classify_cell(); an edge every point of the cell passes needs no exact test, an edge every point fails empties the wedge.
 __device__ __forceinline__ uint32_t classify_cell_edges(const float* __restrict__ wq, float x0, float x1, float y0, float y1) {
+    // both cross products are affine in (x, y): over the rectangle they range over (value at the centre) -/+ (extent), which costs a
+    // third of four corner evaluations.  Float error << guard for |p| up to the 1200 m "absorbing" edge cells.
     const float guard = 2e-3f;
-    float cr_min = INFINITY, cr_max = -INFINITY, cl_min = INFINITY, cl_max = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float qx = ((k & 1) ? x1 : x0) - wq[0], qy = ((k & 2) ? y1 : y0) - wq[1];
-        const float cr = wq[4] * qy - wq[5] * qx, cl = qx * wq[3] - qy * wq[2];
-        cr_min = fminf(cr_min, cr); cr_max = fmaxf(cr_max, cr);
-        cl_min = fminf(cl_min, cl); cl_max = fmaxf(cl_max, cl);
-    }
-    if (cr_max < -guard || cl_max < -guard) return 0u;  // outside
-    return 1u | ((cr_min > guard) ? 0u : 2u) | ((cl_min > guard) ? 0u : 4u);
+    const float hx = 0.5f * (x1 - x0), hy = 0.5f * (y1 - y0);
+    const float qx = 0.5f * (x0 + x1) - wq[0], qy = 0.5f * (y0 + y1) - wq[1];
+    const float cr = wq[4] * qy - wq[5] * qx, cr_e = fabsf(wq[4]) * hy + fabsf(wq[5]) * hx;
+    const float cl = qx * wq[3] - qy * wq[2], cl_e = fabsf(wq[3]) * hx + fabsf(wq[2]) * hy;
+    if (cr + cr_e < -guard || cl + cl_e < -guard) return 0u;  // outside
+    return 1u | ((cr - cr_e > guard) ? 0u : 2u) | ((cl - cl_e > guard) ? 0u : 4u);
 }
 
 // camera wedge: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W (f64, no FMA)
@@ -724,8 +722,27 @@ static int launch_fused(const FusedArgs& args, const TableLayout& T, unsigned ch
     return MSC_OK;
 }
 // tables (prepared boxes, projection, wedges, wedge classes -> workspace), launched before either streaming kernel
+// one side stream per device: the class kernel runs beside the cull-id kernel (both only need the table kernel's output)
+struct SideStream { bool made = false; cudaStream_t s; cudaEvent_t fork, join; };
+static SideStream g_side[64];
+static int side_stream(SideStream** out) {
+    int dev = 0;
+    MSC_CUDA(cudaGetDevice(&dev));
+    SideStream& S = g_side[dev & 63];
+    if (!S.made) {
+        MSC_CUDA(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
+        MSC_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+        MSC_CUDA(cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming));
+        S.made = true;
+    }
+    *out = &S;
+    return MSC_OK;
+}
+
+// `side` != nullptr: the class kernel goes to the side stream and the caller joins it (cudaStreamWaitEvent(stream, side->join))
+// before its streaming kernel
 static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, bool fov, bool per_edge,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, SideStream* side = nullptr) {
     const int ncc = args.L.cull_dim * args.L.cull_dim;
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
@@ -738,8 +755,15 @@ static int launch_tables(const FusedArgs& args, const TableLayout& T, unsigned c
     }
     if (fov) {
         const long long cells = (long long)args.in.n_samples * (ncc + (per_edge ? args.L.inner_dim * args.L.inner_dim : 0));
-        fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(args, T, ws, per_edge);
+        cudaStream_t cs = stream;
+        if (side) {
+            MSC_CUDA(cudaEventRecord(side->fork, stream));
+            MSC_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+            cs = side->s;
+        }
+        fused_fovcls_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, cs>>>(args, T, ws, per_edge);
         MSC_CUDA(cudaGetLastError());
+        if (side) MSC_CUDA(cudaEventRecord(side->join, side->s));
         ++g_last_launches;
     }
     return MSC_OK;
@@ -780,8 +804,10 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
     g_last_window = args.L.win_w;
     g_last_smem = args.L.total_bytes;
     g_last_tile_pts = tile_pts; g_last_stages = 2; g_last_threads = threads;
-    int rc = launch_tables(args, T, ws, n_boxes_total, fov, true, stream);
+    SideStream* side = nullptr;
+    int rc = side_stream(&side);
     if (rc != MSC_OK) return rc;
+    if ((rc = launch_tables(args, T, ws, n_boxes_total, fov, true, stream, side)) != MSC_OK) return rc;
     const size_t ncc = (size_t)args.L.cull_dim * args.L.cull_dim;
     MSC_CUDA(cudaMemsetAsync(ws + T.cullids_off, 0xff, (size_t)args.in.n_samples * ncc * 4, stream));  // kCullEmpty
     if (n_boxes_total > 0 && args.L.max_boxes > 0) {
@@ -790,6 +816,7 @@ static int dispatch_stream(int shape, FusedArgs& args, const TableLayout& T, uns
         MSC_CUDA(cudaGetLastError());
         ++g_last_launches;
     }
+    if (fov) MSC_CUDA(cudaStreamWaitEvent(stream, side->join, 0));  // the class tables are ready
     if ((rc = time_begin(stream)) != MSC_OK) return rc;
     if ((rc = launch_stream_kernel(shape, args, T, ws, grid, fov, fast, stream)) != MSC_OK) return rc;
     ++g_last_launches;
