@@ -106,8 +106,9 @@ int msc_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_ma
  * Replaces: LiDARAgent._preprocess_point_cloud / _segment_ground (lidar_agent.py:103-132) and the raster
  * half of _generate_multi_layer_bev (:539-560) for batches, plus the [EXT] rows e1-e5 of SURVEY.md
  * section 8(a) (devkit from_file_multisweep, points_in_box, get_sample_data/view_points/box_in_image).
- * Two launches: a small table kernel (prepared boxes, projection, camera wedges, per-cell wedge classes -> workspace)
- * and the streaming kernel.  workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned.
+ * Four launches: three small table kernels (prepared boxes + projection + camera wedges; per-cell wedge / edge classes, on an
+ * internal side stream joined by an event; candidate-box ids per cull cell -> workspace) and the streaming kernel.
+ * workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned.  Calls on one host thread at a time (options are process-wide).
  */
 size_t msc_fused_workspace_bytes(const msc_params* params, int32_t n_samples, int32_t n_boxes);
 int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
