@@ -153,6 +153,9 @@ def test_fused_other_grid_and_exact_division_path(engine):
     check_fused(engine, s, params=GeomParams(range_max=30.0, bev_range=32.0, bev_res=128, z_max=3.0, ground_z=-1.0, remove_close_radius=2.5))
     check_fused(engine, s)
     assert _capi.get_option("last_fastdiv") == 1
+    # a grid smaller than the fine edge-class table of the streaming kernel: the table then covers every cell, clipped edge cells included
+    check_fused(engine, s, params=GeomParams(range_max=9.5, bev_range=10.0, bev_res=40))
+    check_fused(engine, s, params=GeomParams(range_max=24.0, bev_range=16.0, bev_res=48))   # range beyond the grid: points clip into edge cells
 
 
 def test_fused_many_sweeps_and_camera_counts(engine):
