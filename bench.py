@@ -46,9 +46,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fov", type=int, default=1)
     ap.add_argument("--window", type=int, default=0)
-    ap.add_argument("--config", type=int, default=7, help="launch shape of the fused kernel (see msc_fused_set_option)")
+    ap.add_argument("--config", type=int, default=0, help="streaming kernel: 0 = auto, 9 = stream3.cu, 7 = fused_stream.cu")
+    ap.add_argument("--split", type=int, default=0, help="CTAs per sample (0 = auto)")
     ap.add_argument("--cull-shift", type=int, default=-1)
-    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: knock out stages of the fused kernel (results invalid)")
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")
     return ap.parse_args()
 
@@ -188,7 +188,7 @@ def main():
     _capi.set_option("window", args.window)
     _capi.set_option("config", args.config)
     _capi.set_option("cull_shift", args.cull_shift)
-    _capi.set_option("debug_skip", args.debug_skip)
+    _capi.set_option("split", args.split)
 
     strong_total = {"mini404": 404, "trainval": 34149}.get(args.workload, 0)
     if strong_total:
@@ -330,7 +330,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "stream_evidence_kernel" if args.config >= 7 else "fused_evidence_kernel", "kernel_ms": kavg_ms,
+                "kernel": "stream3_kernel" if _capi.get_option("last_config") == 9 else "stream_evidence_kernel", "kernel_ms": kavg_ms,
                 "call_ms": call_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
     cpu = None
     if not args.no_cpu and world == 1:
@@ -345,8 +345,8 @@ def main():
             "config": {"workload": wname, "samples_per_gpu": S, "total_samples": total_samples, "points_per_step_per_gpu": hb.n_points,
                        "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (hb.n_points * 20 / 1e9),
                        "fov_counts": bool(args.fov), "bev_window_cells": _capi.get_option("last_window"),
-                       "tile_pts": _capi.get_option("tile_pts"), "stages": _capi.get_option("stages"),
-                       "threads": _capi.get_option("threads")},
+                       "tile_pts": _capi.get_option("tile_pts"), "threads": _capi.get_option("threads"),
+                       "kernel_config": _capi.get_option("last_config"), "ctas_per_sample": _capi.get_option("last_split")},
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

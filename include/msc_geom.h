@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MSC_ABI_VERSION 1
+#define MSC_ABI_VERSION 2
 #define MSC_MAX_CAMS 8
 #define MSC_MAX_BOXES_FUSED 255 /* per sample, fused kernel (cull cells hold u8 box ids; 0xff = empty) */
 #define MSC_STATS_STRIDE 16
@@ -49,7 +49,7 @@ typedef struct {
     int32_t image_h;           /* 900  */
     int32_t n_cams;            /* 6, <= MSC_MAX_CAMS */
     uint32_t fov_keep_mask;    /* 0: count per-camera wedge membership only; else keep points in any set camera */
-    int32_t centroid_shift;    /* fraction bits of the fixed-point centroid sums (20 for range_max <= 60)  */
+    int32_t centroid_shift;    /* fraction bits of the fixed-point centroid sums, <= 17 (|c| < 64 m)       */
     int32_t intensity_shift;   /* fraction bits of the fixed-point intensity sums (8)                     */
     /* square-root-free range thresholds on s = x*x + y*y (host: msc_geom.geometry.sqrt_thresholds) */
     float s_lo;                /* smallest f32 s with sqrtf(s) > range_min */
@@ -63,7 +63,8 @@ typedef struct {
     int32_t n_samples;
     int32_t max_boxes_per_sample;    /* max over samples of the box count (sizes the smem box tables)     */
     int32_t n_boxes;                 /* total boxes in the batch (= sample_box_off[n_samples])            */
-    int32_t reserved_;
+    int32_t points_per_sample_hint;  /* typical points per sample (0 = unknown: a 10-sweep sample is assumed); only steers how a batch
+                                        smaller than the SM count is split over CTAs, never the results                       */
     const float* points;             /* [n_points_padded, 5] raw sweep rows                               */
     const int32_t* sample_sweep_off; /* [n_samples + 1] index into the sweep arrays                       */
     const uint32_t* sweep_start;     /* [n_sweeps] first point of the sweep (multiple of 4)               */
@@ -106,27 +107,36 @@ int msc_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_ma
  * Replaces: LiDARAgent._preprocess_point_cloud / _segment_ground (lidar_agent.py:103-132) and the raster
  * half of _generate_multi_layer_bev (:539-560) for batches, plus the [EXT] rows e1-e5 of SURVEY.md
  * section 8(a) (devkit from_file_multisweep, points_in_box, get_sample_data/view_points/box_in_image).
- * Four launches: three small table kernels (prepared boxes + projection + camera wedges; per-cell wedge / edge classes, on an
- * internal side stream joined by an event; candidate-box ids per cull cell -> workspace) and the streaming kernel.
- * workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned.  Calls on one host thread at a time (options are process-wide).
+ * Four launches: three small table kernels (prepared boxes + projection + camera wedges; per-cell edge classes, on the context's
+ * side stream joined by an event; candidate-box ids per cull cell -> workspace) and the streaming kernel.  A batch with fewer samples
+ * than the device has SMs is split over several CTAs per sample (integer accumulators: results do not depend on the split).
+ * workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned, owned by the caller, one per stream in flight.
+ *
+ * Context: options, the side stream, the timing ring and the facts about the last call live in an msc_fused_ctx, created on the current
+ * device.  Calls that share a context are serialised by it; contexts are independent, so host threads / streams / devices that each
+ * own one never share mutable state.
  */
-size_t msc_fused_workspace_bytes(const msc_params* params, int32_t n_samples, int32_t n_boxes);
-int msc_fused_evidence_batch(const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
+typedef struct msc_fused_ctx msc_fused_ctx;
+int msc_fused_create(msc_fused_ctx** out);
+int msc_fused_destroy(msc_fused_ctx* ctx);
+size_t msc_fused_workspace_bytes(const msc_fused_ctx* ctx, const msc_params* params, int32_t n_samples, int32_t n_boxes);
+int msc_fused_evidence_batch(msc_fused_ctx* ctx, const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
- * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv",
- * "cull_shift" (-1 auto), "config" (launch shape: 7 = second-generation kernel fused_stream.cu, the default; 8 = its 512-thread
- * shape; 6 and 0 = two shapes of the first-generation kernel fused_evidence.cu), "time_kernel".  get: also "last_window", "last_smem", "tile_pts",
- * "stages", "threads", "last_launches". */
-int msc_fused_set_option(const char* key, int32_t value);
-int msc_fused_get_option(const char* key, int32_t* value);
+ * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv", "cull_shift" (-1 auto),
+ * "config" (0 = auto, the default: stream3.cu when the batch is split over CTAs, fused_stream.cu otherwise; 9 / 7 force one;
+ * fov_keep_mask != 0 always takes fused_stream.cu),
+ * "split" (CTAs per sample, 0 = auto), "time_kernel".  get: also "last_window", "last_smem", "last_fastdiv", "last_split", "last_grid",
+ * "last_config", "tile_pts", "threads", "last_launches". */
+int msc_fused_set_option(msc_fused_ctx* ctx, const char* key, int32_t value);
+int msc_fused_get_option(msc_fused_ctx* ctx, const char* key, int32_t* value);
 
 /* Measurement aid (no reference counterpart): with option "time_kernel" = 1 every msc_fused_evidence_batch call brackets its
- * streaming kernel -- not the small table kernels before it -- with CUDA events on the caller's stream (a ring of 64 pairs).
+ * streaming kernel -- not the small table kernels before it -- with CUDA events on the caller's stream (a ring of 64 pairs per context).
  * Copies the durations in ms of the most recent n timed calls, oldest first, to out_ms_host after synchronising on their end
  * events.  Returns the number written (<= n) or a negative msc_status.  get_option("last_launches") = kernels the last call launched. */
-int msc_fused_kernel_times(float* out_ms_host, int32_t n);
+int msc_fused_kernel_times(msc_fused_ctx* ctx, float* out_ms_host, int32_t n);
 
 /*
  * Materialised multi-sweep aggregation (devkit LidarPointCloud.from_file_multisweep, App. A.1) for one

@@ -1,16 +1,15 @@
-// fused_common.cuh -- types and device helpers shared by the two generations of the streaming kernel
-// (fused_evidence.cu: configs 0 and 6; fused_stream.cu: configs 7, the default, and 8).
+// fused_common.cuh -- types and device helpers shared by the table kernels (fused_evidence.cu) and the two streaming kernels
+// (stream3.cu: config 9, the default; fused_stream.cu: config 7, the previous generation, which still serves fov_keep_mask != 0).
 #pragma once
 #include "msc_common.cuh"
 
 namespace msc {
 
-constexpr int kMaxSweepsSmem = 64;  // per-sample sweep table cached in smem (larger samples read it from global)
 constexpr int kBoxStride = 20;      // floats per box record: 80 B stride makes the four LDS.128 conflict-free
 
 constexpr uint32_t kCullEmpty = 0xffffffffu;  // no candidate box in this cell
 constexpr uint32_t kCullAll = 0xfefefefeu;    // more than four boxes touch the cell: test every box
-constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axes x 2 twelve-bit limbs; the odd
+constexpr int kAccWords = 9;                  // per-box accumulators: count, min s, 3 axis words, 3 carry words, pad; the odd
                                               // stride spreads the same word of different boxes over all 32 banks
 constexpr int kMaxWarps = 32;
 constexpr int kInnerMax = 50;  // fused_stream.cu: side of the fine (one BEV cell) edge-class grid around the sensor
@@ -31,7 +30,7 @@ struct FusedArgs {
     // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
     float two_r, resf, rcp_two_r, cscale, iscale;
     int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
-    uint32_t debug_skip;    // profiling only (option "debug_skip"): 1 global atomics, 2 box loop, 4 window atomics, 8 box accumulate
+    int32_t split;          // stream3.cu: CTAs that share one sample (1 = a sample per CTA)
 };
 
 // BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
@@ -52,15 +51,65 @@ __device__ __forceinline__ int bev_cell(float c, float r, float two_r, float rcp
     return min(max(i, 0), res_m1);
 }
 
+// Packed pairs of f32 (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per lane and issue slot; each half is
+// bit-identical to the scalar instruction, so the arithmetic contract of msc_common.cuh is unchanged).
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// bev_cell() of x and y in one packed pass (same operations, same order, per half)
+template <bool FASTDIV>
+__device__ __forceinline__ void bev_cell_xy(float x, float y, float r, float two_r, float rcp_two_r, float resf, int res_m1, int& ix, int& iy) {
+    const unsigned long long a = f2_add(f2_pack(x, y), f2_pack(r, r));
+    unsigned long long q;
+    if (FASTDIV) {
+        const unsigned long long rc = f2_pack(rcp_two_r, rcp_two_r);
+        const unsigned long long q0 = f2_mul(a, rc);
+        const unsigned long long rem = f2_fma(f2_pack(-two_r, -two_r), q0, a);
+        q = f2_fma(rem, rc, q0);
+    } else {
+        float ax, ay;
+        f2_unpack(a, ax, ay);
+        q = f2_pack(__fdiv_rn(ax, two_r), __fdiv_rn(ay, two_r));
+    }
+    float tx, ty;
+    f2_unpack(f2_mul(q, f2_pack(resf, resf)), tx, ty);
+    ix = min(max(__float2int_rz(tx), 0), res_m1);
+    iy = min(max(__float2int_rz(ty), 0), res_m1);
+}
+
 struct TableLayout {  // offsets (bytes) into the workspace
-    size_t counter_off, boxprep_off, wedge_off, fovcls_off, edgecls_off, innercls_off, cullids_off, total;
+    size_t counter_off, boxprep_off, wedge_off, edgecls_off, innercls_off, cullids_off;
+    size_t boxscr_off, splitstats_off;  // stream3.cu, split > 1: per-box (count | min << 32, 3 biased sums) u64 x 4, per-sample stats + ticket
+    size_t total;
 };
 
-// fused_stream.cu (configs 7-8): bytes of its per-CTA state block, and its launcher
+// fused_stream.cu (config 7): bytes of its per-CTA state block, and its launcher
 int stream_misc_bytes();
-void stream_shape_info(int shape, int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
-int launch_stream_kernel(int shape, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast,
-                         cudaStream_t stream);
+void stream_shape_info(int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
+int launch_stream_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream);
+// stream3.cu (config 9)
+int stream3_misc_bytes();
+int stream3_ring_bytes();
+int stream3_queue_bytes();
+int launch_stream3_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream);
 
 // exact wedge test (the definition): q = p - apex, cross(e_right, q) >= 0 and cross(q, e_left) >= 0
 __device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
@@ -140,18 +189,4 @@ __device__ __forceinline__ bool box_contains(const float* __restrict__ boxp, int
     const float kv = __fmaf_rn(b2.w, v2, __fmaf_rn(b2.z, v1, __fmul_rn(b2.y, v0)));
     return iv >= 0.0f && iv <= b3.x && jv >= 0.0f && jv <= b3.y && kv >= 0.0f && kv <= b3.z;
 }
-// Accumulator update of a member point.  Centroid sums: biased non-negative fixed point, two 12-bit limbs per axis,
-// every update a fire-and-forget ATOMS (order-independent, bit-reproducible).
-__device__ __forceinline__ void box_accumulate(const FusedArgs& A, uint32_t* __restrict__ boxacc, int b, float xr, float yr, float zr, float s2) {
-    uint32_t* acc = boxacc + b * kAccWords;
-    atomicAdd(acc + 0, 1u);
-    atomicMin(acc + 1, __float_as_uint(s2));
-    const uint32_t qx = (uint32_t)(__float2int_rn(__fmul_rn(xr, A.cscale)) + A.centroid_bias);
-    const uint32_t qy = (uint32_t)(__float2int_rn(__fmul_rn(yr, A.cscale)) + A.centroid_bias);
-    const uint32_t qz = (uint32_t)(__float2int_rn(__fmul_rn(zr, A.cscale)) + A.centroid_bias);
-    atomicAdd(acc + 2, qx & 4095u); atomicAdd(acc + 3, qx >> 12);
-    atomicAdd(acc + 4, qy & 4095u); atomicAdd(acc + 5, qy >> 12);
-    atomicAdd(acc + 6, qz & 4095u); atomicAdd(acc + 7, qz >> 12);
-}
-
 }  // namespace msc

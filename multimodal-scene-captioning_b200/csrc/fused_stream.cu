@@ -1,4 +1,6 @@
-// fused_stream.cu -- second generation of the streaming kernel (launch shapes "config" 7, the default, and 8).
+// fused_stream.cu -- second generation of the streaming kernel (launch shape "config" 7).  Superseded as the default by stream3.cu
+// (config 9); it still serves fov_keep_mask != 0 (a FOV *filter* needs the per-point wedge classes before the BEV update) and is the
+// shape every change to stream3.cu is compared with bit for bit (tools/sweep_configs.py).
 //
 // Same arithmetic, per point, as fused_evidence.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); what
 // changed is the control structure, because the first generation was instruction-issue bound (ncu: 80 % of issue
@@ -520,9 +522,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     }
 }
 
-// launch shapes: 0 = 1024 threads x 2 points per lane (config 7, the default), 1 = 512 x 4 with the transform in registers (config 8)
+// launch shape: 1024 threads x 2 points per lane
 using Shape0 = StreamShape<1024, 2, false>;
-using Shape1 = StreamShape<512, 4, true>;
 
 template <class C, bool FOV, bool FASTDIV, bool KEEPMASK>
 static int launch_one(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream) {
@@ -532,23 +533,17 @@ static int launch_one(const FusedArgs& args, const TableLayout& T, unsigned char
     MSC_CUDA(cudaGetLastError());
     return MSC_OK;
 }
-template <class C>
-static int launch_shape(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream) {
+
+void stream_shape_info(int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes) {
+    *threads = Shape0::kThreads; *tile_pts = Shape0::kTilePts; *ring_bytes = Shape0::kRingBytes; *queue_bytes = Shape0::kQueueBytes;
+}
+
+int launch_stream_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream) {
+    using C = Shape0;
     if (fov && args.P.fov_keep_mask != 0u)
         return fast ? launch_one<C, true, true, true>(args, T, ws, grid, stream) : launch_one<C, true, false, true>(args, T, ws, grid, stream);
     if (fov) return fast ? launch_one<C, true, true, false>(args, T, ws, grid, stream) : launch_one<C, true, false, false>(args, T, ws, grid, stream);
     return fast ? launch_one<C, false, true, false>(args, T, ws, grid, stream) : launch_one<C, false, false, false>(args, T, ws, grid, stream);
-}
-
-void stream_shape_info(int shape, int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes) {
-    if (shape == 1) { *threads = Shape1::kThreads; *tile_pts = Shape1::kTilePts; *ring_bytes = Shape1::kRingBytes; *queue_bytes = Shape1::kQueueBytes; }
-    else { *threads = Shape0::kThreads; *tile_pts = Shape0::kTilePts; *ring_bytes = Shape0::kRingBytes; *queue_bytes = Shape0::kQueueBytes; }
-}
-
-int launch_stream_kernel(int shape, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast,
-                         cudaStream_t stream) {
-    if (shape == 1) return launch_shape<Shape1>(args, T, ws, grid, fov, fast, stream);
-    return launch_shape<Shape0>(args, T, ws, grid, fov, fast, stream);
 }
 
 }  // namespace msc

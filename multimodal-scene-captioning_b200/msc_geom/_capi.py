@@ -9,7 +9,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 MSC_MAX_CAMS = 8
 MSC_MAX_BOXES_FUSED = 255
 MSC_STATS_STRIDE = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MscError(RuntimeError):
@@ -27,7 +27,7 @@ class MscParams(C.Structure):
 
 class MscBatchIn(C.Structure):
     _fields_ = [
-        ("n_samples", C.c_int32), ("max_boxes_per_sample", C.c_int32), ("n_boxes", C.c_int32), ("reserved_", C.c_int32),
+        ("n_samples", C.c_int32), ("max_boxes_per_sample", C.c_int32), ("n_boxes", C.c_int32), ("points_per_sample_hint", C.c_int32),
         ("points", C.c_void_p),
         ("sample_sweep_off", C.c_void_p), ("sweep_start", C.c_void_p), ("sweep_count", C.c_void_p),
         ("sweep_pose", C.c_void_p), ("sample_box_off", C.c_void_p), ("boxes", C.c_void_p), ("ego_pose", C.c_void_p),
@@ -48,12 +48,14 @@ _PROTOS = {
     "msc_abi_version": (C.c_int, []),
     "msc_last_error": (C.c_char_p, []),
     "msc_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 4),
-    "msc_fused_workspace_bytes": (C.c_size_t, [C.POINTER(MscParams), C.c_int32, C.c_int32]),
-    "msc_fused_evidence_batch": (C.c_int, [C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_void_p,
+    "msc_fused_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "msc_fused_destroy": (C.c_int, [C.c_void_p]),
+    "msc_fused_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(MscParams), C.c_int32, C.c_int32]),
+    "msc_fused_evidence_batch": (C.c_int, [C.c_void_p, C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
-    "msc_fused_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
-    "msc_fused_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
-    "msc_fused_kernel_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32]),
+    "msc_fused_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "msc_fused_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)]),
+    "msc_fused_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "msc_aggregate_sweeps": (C.c_int, [C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "msc_keyframe_filter_split": (C.c_int, [C.POINTER(MscParams), C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -101,7 +103,8 @@ def load():
     return lib
 
 
-DEFAULT_FUSED_CONFIG = 7  # launch shape the library selects by default (fused_evidence.cu: g_opt_config)
+DEFAULT_FUSED_CONFIG = 0  # auto (fused_evidence.cu: msc_fused_ctx::opt_config): stream3.cu when a batch is split over CTAs, else fused_stream.cu
+FUSED_CONFIGS = (9, 7)    # forced: stream3.cu, fused_stream.cu
 
 
 def check(status: int, what: str):
@@ -110,20 +113,64 @@ def check(status: int, what: str):
         raise MscError(f"{what} failed with status {status}: {msg}")
 
 
+class FusedContext:
+    """An msc_fused_ctx: options, side stream and timing ring of one caller (created on the current CUDA device)."""
+
+    def __init__(self):
+        self._lib = load()
+        h = C.c_void_p()
+        check(self._lib.msc_fused_create(C.byref(h)), "msc_fused_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.msc_fused_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        check(self._lib.msc_fused_set_option(self.handle, key.encode(), int(value)), f"set_option({key})")
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int32(0)
+        check(self._lib.msc_fused_get_option(self.handle, key.encode(), C.byref(v)), f"get_option({key})")
+        return int(v.value)
+
+    def kernel_times(self, n: int = 64):
+        """Durations (ms) of the streaming kernel in the most recent calls timed with set_option("time_kernel", 1), oldest first."""
+        buf = (C.c_float * max(n, 1))()
+        got = self._lib.msc_fused_kernel_times(self.handle, buf, int(n))
+        if got < 0:
+            check(got, "msc_fused_kernel_times")
+        return [float(buf[i]) for i in range(got)]
+
+
+_default_ctx = {}
+
+
+def default_context() -> FusedContext:
+    """The context module-level set_option / get_option / kernel_times act on and a GeometryEngine uses unless it is given its own;
+    one per CUDA device."""
+    import torch
+    dev = torch.cuda.current_device()
+    ctx = _default_ctx.get(dev)
+    if ctx is None:
+        ctx = _default_ctx[dev] = FusedContext()
+    return ctx
+
+
 def set_option(key: str, value: int):
-    check(load().msc_fused_set_option(key.encode(), int(value)), f"set_option({key})")
+    default_context().set_option(key, value)
 
 
 def get_option(key: str) -> int:
-    v = C.c_int32(0)
-    check(load().msc_fused_get_option(key.encode(), C.byref(v)), f"get_option({key})")
-    return int(v.value)
+    return default_context().get_option(key)
 
 
 def kernel_times(n: int = 64):
-    """Durations (ms) of the streaming kernel in the most recent calls timed with set_option("time_kernel", 1), oldest first."""
-    buf = (C.c_float * max(n, 1))()
-    got = load().msc_fused_kernel_times(buf, int(n))
-    if got < 0:
-        check(got, "msc_fused_kernel_times")
-    return [float(buf[i]) for i in range(got)]
+    return default_context().kernel_times(n)

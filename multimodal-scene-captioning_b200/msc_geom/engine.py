@@ -42,7 +42,9 @@ class DeviceBatch:
 
     def struct(self) -> MscBatchIn:
         t = self.tensors
-        return MscBatchIn(self.host.n_samples, self.host.max_boxes_per_sample, self.host.n_boxes, 0, *[t[k].data_ptr() for k in _IN_FIELDS])
+        hb = self.host
+        hint = int(hb.sweep_count.sum() // max(hb.n_samples, 1)) if hb.sweep_count.size else 0
+        return MscBatchIn(hb.n_samples, hb.max_boxes_per_sample, hb.n_boxes, min(hint, 2 ** 31 - 1), *[t[k].data_ptr() for k in _IN_FIELDS])
 
 
 @dataclass
@@ -93,12 +95,14 @@ class BatchResult:
 class GeometryEngine:
     """Owns the device, the loaded library and reusable output buffers."""
 
-    def __init__(self, device: Optional[int] = None, params: Optional[GeomParams] = None):
+    def __init__(self, device: Optional[int] = None, params: Optional[GeomParams] = None, own_context: bool = False):
         if not torch.cuda.is_available():
             raise _capi.MscError("GeometryEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _capi.load()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         torch.cuda.set_device(self.device)
+        # options / side stream / timing ring of the fused path; own_context=True gives this engine private ones (one per host thread)
+        self.ctx = _capi.FusedContext() if own_context else _capi.default_context()
         self.params = params or GeomParams()
         sm, smem, maj, mnr = (C.c_int32() for _ in range(4))
         _capi.check(self.lib.msc_device_info(C.byref(sm), C.byref(smem), C.byref(maj), C.byref(mnr)), "msc_device_info")
@@ -166,13 +170,13 @@ class GeometryEngine:
             out = self.alloc_result(db.host, p)
         mp, bi, bo = make_params(p), db.struct(), out.struct()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        need = int(self.lib.msc_fused_workspace_bytes(C.byref(mp), db.host.n_samples, db.host.n_boxes))
+        need = int(self.lib.msc_fused_workspace_bytes(self.ctx.handle, C.byref(mp), db.host.n_samples, db.host.n_boxes))
         ws = self._workspaces.get(stream)
         if ws is None or ws.numel() < need:
             ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
-        _capi.check(self.lib.msc_fused_evidence_batch(C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
+        _capi.check(self.lib.msc_fused_evidence_batch(self.ctx.handle, C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
                                                       C.c_void_p(stream)), "msc_fused_evidence_batch")
-        self.kernel_launches += _capi.get_option("last_launches")  # table kernels + the streaming kernel, counted by the library
+        self.kernel_launches += self.ctx.get_option("last_launches")  # table kernels + the streaming kernel, counted by the library
         return out
 
     # ------------------------------------------------------------------ batched pairwise relation tables ([EXT] e6)

@@ -18,7 +18,7 @@ from tests import oracle_bridge as OB
 IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
 
 
-DEFAULT_CONFIGS = (6, 7, 8)  # first-generation kernel, second-generation kernel (1024 x 2 and 512 x 4 launch shapes)
+DEFAULT_CONFIGS = _capi.FUSED_CONFIGS  # 9: stream3.cu (default), 7: fused_stream.cu (previous generation)
 
 
 def check_fused(eng, samples, params=None, config=None, n_cams=6):
@@ -49,7 +49,7 @@ def check_fused(eng, samples, params=None, config=None, n_cams=6):
     return hb, got
 
 
-@pytest.mark.parametrize("config", [0, 6, 7, 8])
+@pytest.mark.parametrize("config", [9, 7])
 def test_fused_config3_shape(engine, config):
     check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
 
@@ -69,7 +69,7 @@ def test_fused_ragged_and_empty_inputs(engine):
     c = make_sample(32, n_sweeps=1, n_boxes=3)
     c["lidar_sweeps"] = [dict(c["lidar_sweeps"][0], points_raw=c["lidar_sweeps"][0]["points_raw"][:0])]  # no points at all
     d = {"point_cloud": np.random.default_rng(5).normal(0, 12, (5000, 4)).astype(np.float32), "annotations": []}  # plain reference-style sample
-    for cfg in (0, 6, 7, 8):
+    for cfg in DEFAULT_CONFIGS:
         check_fused(engine, [a, b, c, d], config=cfg)
     check_fused(engine, [d])                    # a batch without a single box
     check_fused(engine, [c])                    # ... and one without a single point
@@ -99,7 +99,7 @@ def test_fused_under_declared_max_boxes_sets_the_flag(engine):
     hb = pack_batch(s)
     p = GeomParams()
     cut = dataclasses.replace(hb, max_boxes_per_sample=5)
-    for cfg in (6, 7):
+    for cfg in DEFAULT_CONFIGS:
         _capi.set_option("config", cfg)
         out = engine.run_fused(engine.upload(cut), params=p); torch.cuda.synchronize()
         got = out.to_host()
@@ -170,7 +170,7 @@ def test_fused_many_sweeps_and_camera_counts(engine):
         M[:, 3] += 0.01 * k                         # every sweep gets its own transform
         sw.append(dict(src, points_raw=src["points_raw"][k * 97: k * 97 + 700 + 13 * k], ref_from_sensor=M))
     many = dict(base, lidar_sweeps=sw)
-    for cfg in (0, 6, 7, 8):
+    for cfg in DEFAULT_CONFIGS:
         check_fused(engine, [many, make_sample(96, n_sweeps=2, n_boxes=5)], config=cfg)
     s0 = make_sample(97, n_sweeps=2, n_boxes=9)
     s0["cameras"] = []
@@ -199,7 +199,31 @@ def test_fused_fov_counts_off_and_small_window(engine):
     _capi.set_option("window", 0)
 
 
-@pytest.mark.parametrize("config", [6, 7])
+def test_fused_samples_split_over_ctas(engine):
+    """stream3.cu splits a batch smaller than the SM count over several CTAs per sample (parts merge integer accumulators with global
+    reductions, the last ticket finalises): results must not depend on the split -- forced splits, the automatic one, one keyframe."""
+    import torch
+    s = [make_sample(80 + i, n_sweeps=1 + 4 * (i % 3), n_boxes=15 + 40 * i) for i in range(3)]
+    s.append({"point_cloud": np.random.default_rng(6).normal(0, 12, (3000, 4)).astype(np.float32), "annotations": []})
+    try:
+        for split in (1, 2, 5, 16, 0):
+            _capi.set_option("split", split)
+            check_fused(engine, s, config=9)
+            assert _capi.get_option("last_config") == 9
+            assert _capi.get_option("last_split") == split or split == 0
+        assert _capi.get_option("last_split") > 1                       # 4 samples on 148 SMs: the automatic choice splits
+        check_fused(engine, [make_sample(90, n_sweeps=1, n_boxes=60)], config=9)   # BASELINE config 2: one keyframe
+        assert _capi.get_option("last_grid") > 1
+        _capi.set_option("window", 20)                                    # most cells through the global reductions, split as well
+        _capi.set_option("split", 7)
+        check_fused(engine, s, config=9)
+    finally:
+        _capi.set_option("split", 0)
+        _capi.set_option("window", 0)
+        _capi.set_option("config", _capi.DEFAULT_FUSED_CONFIG)
+
+
+@pytest.mark.parametrize("config", [9, 7])
 def test_fused_full_size_batch_properties(engine, config):
     """BASELINE config-3 batch at the benchmark's size (592 samples, 205.5 M points): size-independent properties, replica
     equality (bit-reproducibility under different scheduling), idempotence, and the oracle on sampled samples."""
