@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short measurements of BASELINE configs 2, 4 and 5")
     ap.add_argument("--fov", type=int, default=1)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--config", type=int, default=0, help="streaming kernel: 0 = auto, 9 = stream3.cu, 7 = fused_stream.cu")
@@ -177,8 +178,10 @@ def main():
     import torch
     import torch.distributed as dist
     from msc_geom import _capi
+    from msc_geom.dist import TableGather, bind_to_gpu_numa
     from msc_geom.engine import GeometryEngine
 
+    numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation: staging buffers and copy threads stay on the GPU's socket
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -189,29 +192,6 @@ def main():
     _capi.set_option("config", args.config)
     _capi.set_option("cull_shift", args.cull_shift)
     _capi.set_option("split", args.split)
-
-    strong_total = {"mini404": 404, "trainval": 34149}.get(args.workload, 0)
-    if strong_total:
-        strong_total = args.total_samples or strong_total
-        lo, hi = shard_range(strong_total, rank, world)
-        S = hi - lo
-    else:
-        S = args.samples_per_gpu
-    n_unique = max(1, min(args.unique, S))
-    reps = (S + n_unique - 1) // n_unique
-    base = rank * 100000
-    hb_u = pack_batch([make_sample(base + i, **wkw) for i in range(n_unique)])
-    db = eng.upload_tiled(hb_u, reps, S if strong_total else None)  # one host copy of the distinct samples, replicated on the device
-    hb = db.host
-    S = hb.n_samples
-    rel_db = rel = None
-    if args.workload == "trainval":  # + pairwise relation table over 200 annotations per sample (BASELINE config 5)
-        ann_u = [{"point_cloud": np.zeros((0, 4), np.float32), "annotations": make_sample(base + 50000 + i, n_sweeps=1, n_boxes=200)["annotations"]}
-                 for i in range(n_unique)]
-        rel_db = eng.upload_tiled(pack_batch(ann_u), reps, S)
-        rel, _ = eng.alloc_relations(rel_db.host)
-    out = eng.alloc_result(hb)
-    abytes = algorithmic_bytes(hb, params)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -219,96 +199,168 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = None
-    if world > 1:
-        tabs = out.table_tensors()
-        gathered = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in tabs]
-
-    def step():
-        eng.run_fused(db, out)
-        if rel_db is not None:
-            eng.run_relations(rel_db, rel)
-        if world > 1:  # NCCL only gathers the small result tables; BEV grids stay sharded
-            for t, g in zip(out.table_tensors(), gathered):
-                dist.all_gather_into_tensor(g, t)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    _capi.set_option("time_kernel", 1)  # CUDA events around the streaming kernel alone, recorded by the library on this stream
-    launches0 = eng.kernel_launches
-    kern_events = []
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ka.record(stream)
-        eng.run_fused(db, out)
-        kb.record(stream)
-        kern_events.append((ka, kb))
-        if rel_db is not None:
-            eng.run_relations(rel_db, rel)
-        if world > 1:
-            for t, g in zip(out.table_tensors(), gathered):
-                dist.all_gather_into_tensor(g, t)
-    e1.record(stream)
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    kern_ms = [a.elapsed_time(b) for a, b in kern_events]
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    total_samples = strong_total if strong_total else world * S
-    value = total_samples * args.steps / (elapsed_ms * 1e-3)
-    gpu_launches = eng.kernel_launches - launches0
-    call_ms = sum(kern_ms) / len(kern_ms)  # whole msc_fused_evidence_batch call: table kernels + streaming kernel
-    own = _capi.kernel_times(min(args.steps, 64))
-    _capi.set_option("time_kernel", 0)
-    kavg_ms = sum(own) / len(own) if own else call_ms  # the dominant (streaming) kernel alone
+        return float(t.item())
 
-    # ---------------------------------------------------------------- end to end: pinned host buffers in, host tables out
+    def run_device_resident(workload: str, steps: int, warmup: int, samples_per_gpu: int, total_override: int = 0, sampler=None):
+        """`steps` timed passes of the hot path over one HBM-resident batch of `workload`, sharded over the ranks; tables gathered with
+        one overlapped collective per step.  Returns the measurement and the pieces the caller reuses (distinct-sample batch, engine state)."""
+        wkw_, wname_ = workload_kwargs(workload)
+        strong = {"mini404": 404, "trainval": 34149}.get(workload, 0)
+        if strong:
+            strong = total_override or strong
+            lo, hi = shard_range(strong, rank, world)
+            S = hi - lo
+        else:
+            S = samples_per_gpu
+        n_unique = max(1, min(args.unique, S))
+        reps = (S + n_unique - 1) // n_unique
+        base = rank * 100000
+        hb_u = pack_batch([make_sample(base + i, **wkw_) for i in range(n_unique)])
+        db = eng.upload_tiled(hb_u, reps, S)  # one host copy of the distinct samples, replicated on the device
+        hb = db.host
+        S = hb.n_samples
+        rel_db = rel = None
+        if workload == "trainval":  # + pairwise relation table over 200 annotations per sample (BASELINE config 5)
+            ann_u = [{"point_cloud": np.zeros((0, 4), np.float32), "annotations": make_sample(base + 50000 + i, n_sweeps=1, n_boxes=200)["annotations"]}
+                     for i in range(n_unique)]
+            rel_db = eng.upload_tiled(pack_batch(ann_u), reps, S)
+            rel, _ = eng.alloc_relations(rel_db.host)
+        _, arena_bytes = eng.table_layout(S, hb.n_boxes, params.n_cams)
+        arena_bytes = int(max_over_ranks(float(arena_bytes)))  # ragged shards: every rank gathers the size of the largest
+        outs = [eng.alloc_result(hb, arena_bytes=arena_bytes) for _ in range(2 if world > 1 else 1)]
+        gat = TableGather(arena_bytes, device=eng.device) if world > 1 else None  # NCCL only moves the small tables; BEV grids stay sharded
+
+        def step(k):
+            out = outs[k % len(outs)]
+            if gat is not None and gat.done[k % 2] is not None:
+                stream.wait_event(gat.done[k % 2])  # the gather that read this arena two steps ago is done
+            eng.run_fused(db, out)
+            if gat is not None:
+                gat.launch(out.table_arena)
+
+        for k in range(max(warmup, 3)):
+            step(k)
+        if gat is not None:
+            gat.wait()
+        barrier()
+        _capi.set_option("time_kernel", 1)  # CUDA events around the streaming kernel alone, recorded by the library on this stream
+        launches0 = eng.kernel_launches
+        call_events, rel_events = [], []
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for k in range(steps):
+            ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ka.record(stream)
+            step(k)
+            kb.record(stream)
+            call_events.append((ka, kb))
+            if rel_db is not None:
+                kc = torch.cuda.Event(enable_timing=True)
+                eng.run_relations(rel_db, rel)
+                kc.record(stream)
+                rel_events.append((kb, kc))
+        if gat is not None:
+            gat.wait()
+        e1.record(stream)
+        barrier()
+        if sampler is not None:
+            sampler.stop()
+        elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+        call_ms = sum(a.elapsed_time(b) for a, b in call_events) / len(call_events)
+        own = _capi.kernel_times(min(steps, 64))
+        _capi.set_option("time_kernel", 0)
+        total = strong if strong else world * S
+        m = {"workload": wname_, "scaling": "strong" if strong else "weak", "total_samples": total, "samples_this_rank": S,
+             "value": total * steps / (elapsed_ms * 1e-3), "unit": UNIT, "ms_per_step": elapsed_ms / steps, "steps": steps,
+             "call_ms": call_ms, "kernel_ms": (sum(own) / len(own)) if own else call_ms, "gpu_launches": eng.kernel_launches - launches0,
+             "kernel_config": _capi.get_option("last_config"), "ctas_per_sample": _capi.get_option("last_split"),
+             "grid": _capi.get_option("last_grid"), "bev_window_cells": _capi.get_option("last_window"),
+             "tile_pts": _capi.get_option("tile_pts"), "threads": _capi.get_option("threads"), "table_arena_bytes": arena_bytes,
+             "points_per_step_this_rank": hb.n_points, "algorithmic_bytes": algorithmic_bytes(hb, params), "n_unique": n_unique, "reps": reps}
+        if rel_events:
+            m["relation_table_ms"] = sum(a.elapsed_time(b) for a, b in rel_events) / len(rel_events)
+            m["relation_table_bytes"] = int(hb.n_samples * (40 * 200 + 10 * 200 * 200))
+        return m, hb_u, reps
+
+    # ---------------------------------------------------------------- the metric: BASELINE config 3, weak scaling, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    main, hb_u, reps = run_device_resident(args.workload, args.steps, args.warmup, args.samples_per_gpu, args.total_samples, sampler)
+    strong_total = main["total_samples"] if main["scaling"] == "strong" else 0
+
+    # ---------------------------------------------------------------- end to end: pinned host buffers in, host tables + BEV out
     e2e = None
     if not args.no_e2e and not strong_total:
-        # one chunk = one copy of the distinct-sample set (loader-format flat buffers) in pinned host memory;
-        # three staging slots / streams so H2D, kernel and D2H of neighbouring chunks overlap
+        # one chunk = one copy of the distinct-sample set (loader-format flat buffers) in a pinned input arena: ONE H2D copy per chunk
+        # into a preallocated device arena, the fused call, then three D2H copies (table arena, two BEV layers); three slots / streams so
+        # H2D, kernel and D2H of neighbouring chunks overlap.  Nothing is allocated inside the timed region.
         n_slots = 3
-        pinned = [eng.pin(hb_u) for _ in range(n_slots)]
+        arenas = [eng.input_arena(hb_u) for _ in range(n_slots)]
+        for a in arenas:
+            a.load(hb_u)
         streams = [torch.cuda.Stream() for _ in range(n_slots)]
         outs = [eng.alloc_result(hb_u) for _ in range(n_slots)]
-        host_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (o.table_tensors() + [o.bev_ci, o.bev_height])]
-                    for o in outs]
-        h2d = sum(int(t.numel() * t.element_size()) for t in pinned[0].values()) * reps
+        host_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (o.table_arena, o.bev_ci, o.bev_height)] for o in outs]
+        h2d = arenas[0].nbytes * reps
         d2h = sum(int(t.numel() * t.element_size()) for t in host_out[0]) * reps
 
         def e2e_step():
             for ci in range(reps):
                 slot = ci % n_slots
                 with torch.cuda.stream(streams[slot]):
-                    dbc = eng.upload(hb_u, pinned=pinned[slot], non_blocking=True)
+                    dbc = arenas[slot].upload(non_blocking=True)
                     eng.run_fused(dbc, outs[slot])
-                    for src, dst in zip(outs[slot].table_tensors() + [outs[slot].bev_ci, outs[slot].bev_height], host_out[slot]):
+                    for src, dst in zip((outs[slot].table_arena, outs[slot].bev_ci, outs[slot].bev_height), host_out[slot]):
                         dst.copy_(src, non_blocking=True)
             for s in streams:
                 s.synchronize()
 
         e2e_step()
         barrier()
+        sampler.start()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step()
+        torch.cuda.synchronize()
+        dt_rank = time.perf_counter() - t0
         barrier()
-        dt = time.perf_counter() - t0
+        sampler.stop()
+        dt = max_over_ranks(dt_rank)
         n_e2e = reps * hb_u.n_samples
+        rates = [h2d * args.e2e_steps / dt_rank / 1e9]
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * n_e2e * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
-    sampler.stop()
+            t = torch.tensor(rates, device="cuda", dtype=torch.float64)
+            allr = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            rates = [float(x.item()) for x in allr]
+        e2e = {"value": world * n_e2e * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "h2d_copies_per_chunk": 1, "d2h_copies_per_chunk": 3, "chunks_per_step": reps, "per_rank_h2d_gbs": [round(r, 2) for r in rates],
+               "numa": numa}
+
+    # ---------------------------------------------------------------- the other BASELINE configs, one short measurement each
+    extras = []
+    if not args.no_extra and args.workload == "config3":
+        try:
+            m, _, _ = run_device_resident("mini404", 20, 3, 0)   # config 4: 404 samples, 60-120 boxes, strong scaling over the ranks
+            extras.append(m)
+            if world == 1:
+                m, _, _ = run_device_resident("config2", 20, 3, 1)    # config 2 as written: ONE keyframe on one GPU (latency; the sample is split over CTAs)
+                m["latency_us_per_call"] = 1e3 * m["call_ms"]
+                extras.append(m)
+                m, _, _ = run_device_resident("config2", 20, 3, 592)  # ... and a batch of keyframes (throughput)
+                extras.append(m)
+            if world == 8:
+                m, _, _ = run_device_resident("trainval", 5, 3, 0)   # config 5: 34,149 samples + 200-annotation relation tables, 8 GPUs
+                extras.append(m)
+        except Exception as e:  # noqa: BLE001 -- an extra must not take the headline down with it
+            extras.append({"error": repr(e)})
 
     if rank != 0:
         if world > 1:
@@ -321,6 +373,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kavg_ms, abytes = main["kernel_ms"], main["algorithmic_bytes"]
     achieved = abytes / (kavg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")
@@ -329,9 +382,10 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    kname = "stream3_kernel" if main["kernel_config"] == 9 else "stream_evidence_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "stream3_kernel" if _capi.get_option("last_config") == 9 else "stream_evidence_kernel", "kernel_ms": kavg_ms,
-                "call_ms": call_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
+                "traffic_source": "profiles/fused_traffic.json (one ncu --set full capture of the same launch shape, not this run)",
+                "kernel": kname, "kernel_ms": kavg_ms, "call_ms": main["call_ms"], "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
     cpu = None
     if not args.no_cpu and world == 1:
         n_cpu = args.cpu_samples or 16 * cores  # ~2 s wall on 16 threads = ~30 s of CPU work on the bounded sample
@@ -339,15 +393,24 @@ def main():
         v1, _ = cpu_oracle_throughput(hb_u, params, 8, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": v1,
                "sample": f"{n_cpu} samples of the same workload, scalar C oracle (oracle/c/msc_oracle.c), {cores} threads, {dt:.1f} s wall"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong_total else "weak", "vs_baseline": None,
-            "dtype": "f32+f64", "data": f"synthetic ({n_unique} distinct seeded samples per rank tiled x{reps}, distinct memory)",
-            "config": {"workload": wname, "samples_per_gpu": S, "total_samples": total_samples, "points_per_step_per_gpu": hb.n_points,
-                       "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (hb.n_points * 20 / 1e9),
-                       "fov_counts": bool(args.fov), "bev_window_cells": _capi.get_option("last_window"),
-                       "tile_pts": _capi.get_option("tile_pts"), "threads": _capi.get_option("threads"),
-                       "kernel_config": _capi.get_option("last_config"), "ctas_per_sample": _capi.get_option("last_split")},
-            "e2e": e2e, "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu}
+        ref_py = os.path.join(ROOT, "profiles", "r2_cpu_baseline_reference_python.json")
+        if os.path.exists(ref_py):  # the reference's own Python functions, timed where /root/reference exists (tools/cpu_baseline_reference.py)
+            try:
+                cpu["reference_python"] = json.load(open(ref_py))
+            except Exception:
+                pass
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": main["scaling"], "vs_baseline": None,
+            "dtype": "f32+f64", "data": f"synthetic ({main['n_unique']} distinct seeded samples per rank tiled x{main['reps']}, distinct memory)",
+            "config": {"workload": main["workload"], "samples_per_gpu": main["samples_this_rank"], "total_samples": main["total_samples"],
+                       "points_per_step_per_gpu": main["points_per_step_this_rank"],
+                       "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (main["points_per_step_this_rank"] * 20 / 1e9),
+                       "fov_counts": bool(args.fov), "bev_window_cells": main["bev_window_cells"], "tile_pts": main["tile_pts"],
+                       "threads": main["threads"], "kernel_config": main["kernel_config"], "ctas_per_sample": main["ctas_per_sample"],
+                       "table_gather": "one all_gather_into_tensor of the table arena per step on a side stream (double-buffered)" if world > 1 else "none (1 GPU)",
+                       "table_arena_bytes": main["table_arena_bytes"]},
+            "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "extra_workloads": extras}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,8 +1,8 @@
 """Multi-GPU plumbing: samples are independent (the reference's only many-sample loop touches one sample per
 iteration, src/evaluation_framework.py:534-556), so a batch is split into contiguous blocks, one per rank, each
-rank runs the fused path on its shard with no data-path collective, and ONE all_gather moves the fixed-stride
-per-sample result tables (boxes padded to `max_boxes`).  BEV grids stay sharded.  Works with NCCL (device
-tensors) and gloo (host tensors, used by the CPU tests)."""
+rank runs the fused path on its shard with no data-path collective, and ONE all_gather per step moves the shard's
+table arena (the six small result tables in one buffer, padded to the largest shard) on a side stream.  BEV grids
+stay sharded.  Works with NCCL (device tensors) and gloo (host tensors, used by the CPU tests)."""
 from __future__ import annotations
 
 from typing import Dict, List, Sequence, Tuple
@@ -19,38 +19,121 @@ def shard_range(n_samples: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(lo + per, n_samples)
 
 
-def pad_tables(host: Dict[str, np.ndarray], n_samples: int, n_cams: int, max_boxes: int, per_rank: int) -> Dict[str, torch.Tensor]:
-    """Fixed-stride tables [per_rank, max_boxes, ...] + n_boxes column, from the ragged per-box arrays of one shard."""
-    off = host["sample_box_off"]
-    out = {
-        "n_boxes": torch.zeros(per_rank, dtype=torch.int32),
-        "box_count": torch.zeros((per_rank, max_boxes), dtype=torch.int32),
-        "box_nearest": torch.full((per_rank, max_boxes), float("inf"), dtype=torch.float32),
-        "box_centroid": torch.zeros((per_rank, max_boxes, 3), dtype=torch.float32),
-        "proj_visible": torch.zeros((per_rank, max_boxes, n_cams), dtype=torch.uint8),
-        "proj_extent": torch.zeros((per_rank, max_boxes, n_cams, 4), dtype=torch.float32),
-        "stats": torch.zeros((per_rank, 16), dtype=torch.int32),
-    }
-    for i in range(n_samples):
-        b0, b1 = int(off[i]), int(off[i + 1])
-        nb = b1 - b0
-        out["n_boxes"][i] = nb
-        out["box_count"][i, :nb] = torch.from_numpy(host["box_count"][b0:b1].view(np.int32))
-        out["box_nearest"][i, :nb] = torch.from_numpy(host["box_nearest"][b0:b1])
-        out["box_centroid"][i, :nb] = torch.from_numpy(host["box_centroid"][b0:b1])
-        out["proj_visible"][i, :nb] = torch.from_numpy(host["proj_visible"][b0:b1])
-        out["proj_extent"][i, :nb] = torch.from_numpy(host["proj_extent"][b0:b1])
-        out["stats"][i] = torch.from_numpy(host["stats"][i].view(np.int32))
+def table_shapes(n_samples: int, n_boxes: int, n_cams: int) -> dict:
+    """dtype / shape of the six small result tables of a shard (the views BatchResult holds into its table arena)."""
+    return {"box_count": (torch.int32, (n_boxes,)), "box_nearest": (torch.float32, (n_boxes,)), "box_centroid": (torch.float32, (n_boxes, 3)),
+            "proj_visible": (torch.uint8, (n_boxes, n_cams)), "proj_extent": (torch.float32, (n_boxes, n_cams, 4)),
+            "stats": (torch.int32, (n_samples, 16))}
+
+
+def rank_layout(n_samples: int, n_boxes: int, n_cams: int) -> dict:
+    """Arena layout of one rank's shard (offsets from GeometryEngine.table_layout + shapes), the argument of split_arena()."""
+    from .engine import GeometryEngine
+    lay, size = GeometryEngine.table_layout(n_samples, n_boxes, n_cams)
+    lay = dict(lay)
+    lay["shapes"] = table_shapes(n_samples, n_boxes, n_cams)
+    lay["bytes"] = size
+    return lay
+
+
+def pack_tables_host(tables: Dict[str, np.ndarray], layout: dict, arena_bytes: int) -> torch.Tensor:
+    """Host-side twin of the device arena (CPU tests of the gather path): the ragged per-box arrays of one shard at the arena offsets."""
+    arena = torch.zeros(arena_bytes, dtype=torch.uint8)
+    for name, (dtype, shape) in layout["shapes"].items():
+        o, n = layout[name]
+        if n:
+            src = np.ascontiguousarray(tables[name])
+            arena[o:o + n] = torch.from_numpy(src.view(np.uint8).reshape(-1))
+    return arena
+
+
+class TableGather:
+    """ONE collective per step, off the critical path: the shard's table arena (GeometryEngine.alloc_result: the six small tables in
+    one buffer, padded to the largest shard) is all-gathered on a side stream into one of two output buffers, so the gather of step k
+    overlaps the streaming kernel of step k + 1.  `launch(arena)` orders the gather after everything queued on the current stream;
+    `wait()` makes the current stream wait for every gather in flight.  NCCL for device tensors, gloo for host tensors (CPU tests)."""
+
+    def __init__(self, arena_bytes: int, device=None, depth: int = 2):
+        self.world = dist.get_world_size()
+        self.device = device
+        self.cuda = device is not None and torch.device(device).type == "cuda"
+        self.arena_bytes = arena_bytes
+        self.bufs = [torch.empty(self.world * arena_bytes, dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.k = 0
+        if self.cuda:
+            self.side = torch.cuda.Stream(device=device)
+            self.done = [None] * depth
+
+    def launch(self, arena: torch.Tensor) -> torch.Tensor:
+        slot = self.k % len(self.bufs)
+        self.k += 1
+        out = self.bufs[slot]
+        if not self.cuda:
+            dist.all_gather_into_tensor(out, arena.contiguous())
+            return out.view(self.world, self.arena_bytes)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)          # the tables of this step are complete
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(out, arena)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[slot] = ev
+        return out.view(self.world, self.arena_bytes)
+
+    def wait(self) -> None:
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self.done:
+                if ev is not None:
+                    cur.wait_event(ev)
+
+
+def split_arena(buf: torch.Tensor, rank_layouts: Sequence[dict]) -> List[Dict[str, torch.Tensor]]:
+    """Views of a gathered [world, arena_bytes] buffer as per-rank tables; rank_layouts[r] = GeometryEngine.table_layout(...)[0] plus
+    a "shapes" entry {name: (dtype, shape)} for rank r's shard."""
+    out = []
+    for r, lay in enumerate(rank_layouts):
+        row, tabs = buf[r], {}
+        for name, (dtype, shape) in lay["shapes"].items():
+            o, n = lay[name]
+            tabs[name] = row[o:o + n].view(dtype).view(shape)
+        out.append(tabs)
     return out
 
 
-def gather_tables(tables: Dict[str, torch.Tensor], device=None) -> Dict[str, torch.Tensor]:
-    """all_gather of every table along a new leading rank axis; returns [world * per_rank, ...] tensors on every rank."""
-    world = dist.get_world_size()
-    out = {}
-    for k, t in tables.items():
-        t = t.contiguous() if device is None else t.to(device).contiguous()
-        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)  # rank-major concat
-        dist.all_gather_into_tensor(buf, t)
-        out[k] = buf
-    return out
+def gpu_numa_node(index: int) -> int:
+    """NUMA node of CUDA device `index` from sysfs (-1 when the platform does not say)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        return int(open(path).read().strip())
+    except Exception:
+        return -1
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pin this process (and therefore the pinned buffers it first-touches and its copy-issuing threads) to the cores of the NUMA node the
+    GPU hangs off, so eight ranks do not stage through one socket.  Returns what was done, for the bench record."""
+    import os
+    node = gpu_numa_node(index)
+    info = {"numa_node": node, "bound": False}
+    if node < 0:
+        return info
+    try:
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)
+    return info

@@ -63,6 +63,7 @@ class BatchResult:
     bev_ci: torch.Tensor
     bev_height: torch.Tensor
     stats: torch.Tensor
+    table_arena: Optional[torch.Tensor] = None   # the six small tables above are views into this one buffer (one copy / one collective)
 
     def struct(self) -> MscBatchOut:
         return MscBatchOut(self.box_count.data_ptr(), self.box_nearest.data_ptr(), self.box_centroid.data_ptr(),
@@ -90,6 +91,47 @@ class BatchResult:
             out["bev_intensity_sum"] = (ci[..., 1].astype(np.float64) / float(1 << self.intensity_shift)).astype(np.float32)
             out["bev_height"] = self.bev_height.cpu().numpy()
         return out
+
+
+class InputArena:
+    """One pinned host buffer and one device buffer holding a batch's twelve input arrays at fixed offsets (see
+    GeometryEngine.input_arena).  `load(hb)` copies a batch of the same shape into the pinned side (the step a real loader replaces by
+    reading files straight into `host_view("points")`, msc_geom.io.stage_batch); `upload()` is one async copy."""
+
+    def __init__(self, eng: "GeometryEngine", hb: HostBatch):
+        self.eng = eng
+        al = lambda v: (v + 255) & ~255
+        off, self.layout = 0, {}
+        for k in _IN_FIELDS:
+            a = getattr(hb, k)
+            self.layout[k] = (off, int(a.nbytes), a.dtype, a.shape)
+            off = al(off + int(a.nbytes))
+        self.nbytes = max(off, 256)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=eng.device)
+        self.meta = hb
+        self._host_np = self.host.numpy()
+        self.tensors = {}
+        for k, (o, n, dt, shape) in self.layout.items():
+            tdt = _NP2TORCH[np.dtype(dt)]
+            self.tensors[k] = self.dev[o:o + n].view(tdt).view(shape) if n else torch.empty(shape, dtype=tdt, device=eng.device)
+
+    def host_view(self, k: str) -> np.ndarray:
+        o, n, dt, shape = self.layout[k]
+        return self._host_np[o:o + n].view(dt).reshape(shape)
+
+    def load(self, hb: HostBatch) -> None:
+        for k, (o, n, dt, shape) in self.layout.items():
+            a = getattr(hb, k)
+            if a.shape != shape:
+                raise _capi.MscError(f"InputArena: {k} has shape {a.shape}, the arena was sized for {shape}")
+            if n:
+                self.host_view(k)[...] = a
+        self.meta = hb
+
+    def upload(self, non_blocking: bool = True) -> DeviceBatch:
+        self.dev.copy_(self.host, non_blocking=non_blocking)
+        return DeviceBatch(self.meta, self.tensors)
 
 
 class GeometryEngine:
@@ -150,16 +192,42 @@ class GeometryEngine:
     def pin(hb: HostBatch) -> Dict[str, torch.Tensor]:
         return {k: _as_torch_cpu(getattr(hb, k)).pin_memory() for k in _IN_FIELDS}
 
-    def alloc_result(self, hb: HostBatch, params: Optional[GeomParams] = None) -> BatchResult:
+    def input_arena(self, hb: HostBatch) -> "InputArena":
+        """A reusable staging slot sized for batches shaped like `hb`: one pinned host buffer + one device buffer with the twelve input
+        arrays at fixed 256-byte-aligned offsets, so a batch goes up in ONE cudaMemcpyAsync and nothing is allocated per batch."""
+        return InputArena(self, hb)
+
+    @staticmethod
+    def table_layout(n_samples: int, n_boxes: int, n_cams: int):
+        """Byte offsets of the six small result tables inside one arena (256-byte aligned) and its size: what one D2H copy or one
+        all_gather moves per shard (fixed-stride tables, one collective)."""
+        al = lambda v: (v + 255) & ~255
+        off, lay = 0, {}
+        for name, nbytes in (("box_count", 4 * n_boxes), ("box_nearest", 4 * n_boxes), ("box_centroid", 12 * n_boxes),
+                             ("proj_visible", n_cams * n_boxes), ("proj_extent", 16 * n_cams * n_boxes),
+                             ("stats", 4 * _capi.MSC_STATS_STRIDE * n_samples)):
+            lay[name] = (off, nbytes)
+            off = al(off + nbytes)
+        return lay, max(off, 256)
+
+    def alloc_result(self, hb: HostBatch, params: Optional[GeomParams] = None, arena_bytes: Optional[int] = None) -> BatchResult:
+        """Output buffers for `hb`.  The small tables live in ONE arena (`arena_bytes` pads it, e.g. to the largest shard of a job,
+        so every rank gathers the same size); the BEV layers, which stay sharded, are separate."""
         p = params or self.params
         S, B, Cn, R = hb.n_samples, hb.n_boxes, p.n_cams, p.bev_res
         d = self.device
+        lay, size = self.table_layout(S, B, Cn)
+        arena = torch.zeros(max(size, arena_bytes or 0), dtype=torch.uint8, device=d)
+
+        def view(name, dtype, shape):
+            o, n = lay[name]
+            return arena[o:o + n].view(dtype).view(shape)
         return BatchResult(
             S, Cn, R, p.intensity_shift, hb.sample_box_off.copy(),
-            torch.empty(B, dtype=torch.int32, device=d), torch.empty(B, dtype=torch.float32, device=d),
-            torch.empty((B, 3), dtype=torch.float32, device=d), torch.empty((B, Cn), dtype=torch.uint8, device=d),
-            torch.empty((B, Cn, 4), dtype=torch.float32, device=d), torch.empty((S, R, R, 2), dtype=torch.int32, device=d),
-            torch.empty((S, R, R), dtype=torch.float32, device=d), torch.empty((S, _capi.MSC_STATS_STRIDE), dtype=torch.int32, device=d))
+            view("box_count", torch.int32, (B,)), view("box_nearest", torch.float32, (B,)), view("box_centroid", torch.float32, (B, 3)),
+            view("proj_visible", torch.uint8, (B, Cn)), view("proj_extent", torch.float32, (B, Cn, 4)),
+            torch.empty((S, R, R, 2), dtype=torch.int32, device=d), torch.empty((S, R, R), dtype=torch.float32, device=d),
+            view("stats", torch.int32, (S, _capi.MSC_STATS_STRIDE)), arena)
 
     # ------------------------------------------------------------------ the hot path
     def run_fused(self, db: DeviceBatch, out: Optional[BatchResult] = None, params: Optional[GeomParams] = None) -> BatchResult:

@@ -1,4 +1,4 @@
-"""N>1 path on CPU: world_size-2 gloo run of the sharding + table gather (msc_geom/dist.py)."""
+"""N>1 path on CPU: world_size-2 gloo run of the sharding + the one-collective table-arena gather (msc_geom/dist.py)."""
 import os
 import socket
 
@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from msc_geom.dist import gather_tables, pad_tables, shard_range
+from msc_geom.dist import TableGather, pack_tables_host, rank_layout, shard_range, split_arena
 
 
 def _free_port():
@@ -30,16 +30,26 @@ def _fake_host_tables(lo, hi, n_cams):
 def _worker(rank, world, port, n_samples, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = shard_range(n_samples, rank, world)
-    per = (n_samples + world - 1) // world
-    host, nb_all = _fake_host_tables(lo, hi, 6)
-    g = gather_tables(pad_tables(host, hi - lo, 6, 8, per))
-    ok = g["stats"].shape == (world * per, 16)
-    ok &= bool((g["stats"][:n_samples, 0] == torch.arange(n_samples, dtype=torch.int32)).all())
-    ok &= bool((g["n_boxes"][:n_samples] == torch.from_numpy(nb_all[:n_samples].astype(np.int32))).all())
-    for i in range(n_samples):
-        n = int(g["n_boxes"][i])
-        ok &= bool((g["box_nearest"][i, :n] == i + 0.5).all()) and bool(torch.isinf(g["box_nearest"][i, n:]).all())
+    # every rank knows every shard's shape from the (host-side) box offsets, like bench.py: ragged shards, one arena size for all
+    _, nb_all = _fake_host_tables(0, n_samples, 6)
+    shards = [shard_range(n_samples, r, world) for r in range(world)]
+    layouts = [rank_layout(hi - lo, int(nb_all[lo:hi].sum()), 6) for lo, hi in shards]
+    arena_bytes = max(l["bytes"] for l in layouts)
+    lo, hi = shards[rank]
+    host, _ = _fake_host_tables(lo, hi, 6)
+    tg = TableGather(arena_bytes)                      # gloo: host tensors, same code path as the NCCL one minus the side stream
+    ok = True
+    for step in range(3):                              # double-buffered outputs: consecutive steps land in different buffers
+        host["stats"][:, 1] = step
+        buf = tg.launch(pack_tables_host(host, layouts[rank], arena_bytes))
+        tg.wait()
+        tabs = split_arena(buf, layouts)
+        ok &= buf.shape == (world, arena_bytes)
+        for r, (a, b) in enumerate(shards):
+            ref, _ = _fake_host_tables(a, b, 6)
+            ok &= bool((tabs[r]["stats"][:, 0] == torch.arange(a, b, dtype=torch.int32)).all()) and bool((tabs[r]["stats"][:, 1] == step).all())
+            ok &= np.array_equal(tabs[r]["box_nearest"].numpy(), ref["box_nearest"]) and np.array_equal(tabs[r]["box_centroid"].numpy(), ref["box_centroid"])
+            ok &= np.array_equal(tabs[r]["box_count"].numpy().view(np.uint32), ref["box_count"]) and tabs[r]["proj_visible"].shape == ref["proj_visible"].shape
     t = torch.tensor([1.0 + rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)  # bench.py's max-over-ranks timing reduction
     ok &= float(t) == float(world)
     q.put((rank, bool(ok)))
