@@ -223,13 +223,21 @@ int msc_dbscan(const float* pts, uint32_t n, int32_t pitch, double eps, int32_t 
     db_scan_kernel<<<1, 1024, 0, stream>>>(cell_count, cell_start, (uint32_t)ncells, nullptr);
     db_scatter_kernel<<<nb256, 256, 0, stream>>>(n, cell_of, cell_start, cursor, sorted);
     db_core_kernel<<<nb128, 128, 0, stream>>>(pts, n, pitch, G, eps2, (uint32_t)min_samples, cell_start, cell_count, sorted, core, parent);
-    for (int it = 0; it < 64; ++it) {
+    // atomic-min hooking converges in O(log n) sweeps in practice; a chain of n core points bounds it by n, so the cap grows with n and a
+    // flag that is still set after it is an error, never a silently under-merged labelling
+    const int max_sweeps = 64 + (int)(n / 1024 < 4096 ? n / 1024 : 4096);
+    bool merged = false;
+    for (int it = 0; it < max_sweeps && !merged; ++it) {
         MSC_CUDA(cudaMemsetAsync(flag, 0, 4, stream));
         db_hook_kernel<<<nb128, 128, 0, stream>>>(pts, n, pitch, G, eps2, cell_start, cell_count, sorted, core, parent, flag);
         uint32_t h = 0;
         MSC_CUDA(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, stream));
         MSC_CUDA(cudaStreamSynchronize(stream));
-        if (!h) break;
+        merged = h == 0;
+    }
+    if (!merged) {
+        set_error("msc_dbscan: component merge did not converge in %d sweeps", max_sweeps);
+        return MSC_ERR_LAUNCH;
     }
     db_flatten_kernel<<<nb256, 256, 0, stream>>>(n, core, parent, is_root);
     db_scan_kernel<<<1, 1024, 0, stream>>>(is_root, root_rank, n, flag + 1);

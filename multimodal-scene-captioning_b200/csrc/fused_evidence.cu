@@ -65,6 +65,19 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     float* const boxprep = reinterpret_cast<float*>(ws + T.boxprep_off);
     float* const wedges = reinterpret_cast<float*>(ws + T.wedge_off);
+    // (0) housekeeping that would otherwise be three memsets: the streaming kernel's work counter, the candidate-id table
+    // (kCullEmpty everywhere; fused_cullids_kernel inserts into it after this kernel) and the merge scratch of split samples
+    {
+        const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+        if (gid == 0) *reinterpret_cast<uint32_t*>(ws + T.counter_off) = 0u;
+        uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off);
+        const size_t n_ids = (size_t)A.in.n_samples * (size_t)(A.L.cull_dim * A.L.cull_dim);
+        for (size_t i = gid; i < n_ids; i += nthreads) ids[i] = kCullEmpty;
+        if (A.split > 1) {
+            uint32_t* st = reinterpret_cast<uint32_t*>(ws + T.splitstats_off);
+            for (size_t i = gid; i < (size_t)A.in.n_samples * MSC_STATS_STRIDE; i += nthreads) st[i] = 0u;
+        }
+    }
     // sample of a global box index: binary search in sample_box_off
     auto sample_of_box = [&](int gb) {
         int lo = 0, hi = A.in.n_samples;
@@ -312,26 +325,32 @@ static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLay
         MSC_CUDA(cudaGetLastError());
         ++X->last_launches;
     }
+    // the class kernel runs beside the cull-id kernel on the context's side stream when the batch is big enough for that to pay for the
+    // fork / join events; small batches (latency) keep one stream
+    const bool forked = fov && args.in.n_samples >= 32;
     if (fov) {
-        int rc = side_stream(X);
-        if (rc != MSC_OK) return rc;
-        MSC_CUDA(cudaEventRecord(X->fork, stream));
-        MSC_CUDA(cudaStreamWaitEvent(X->side, X->fork, 0));
+        cudaStream_t cs = stream;
+        if (forked) {
+            int rc = side_stream(X);
+            if (rc != MSC_OK) return rc;
+            MSC_CUDA(cudaEventRecord(X->fork, stream));
+            MSC_CUDA(cudaStreamWaitEvent(X->side, X->fork, 0));
+            cs = X->side;
+        }
         const int per_sample = ncc + args.L.inner_dim * args.L.inner_dim;
         const dim3 fgrid((unsigned)((per_sample + 255) / 256), (unsigned)args.in.n_samples);
-        fused_fovcls_kernel<<<fgrid, 256, 0, X->side>>>(args, T, ws);
+        fused_fovcls_kernel<<<fgrid, 256, 0, cs>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
-        MSC_CUDA(cudaEventRecord(X->join, X->side));
+        if (forked) MSC_CUDA(cudaEventRecord(X->join, X->side));
         ++X->last_launches;
     }
-    MSC_CUDA(cudaMemsetAsync(ws + T.cullids_off, 0xff, (size_t)args.in.n_samples * ncc * 4, stream));  // kCullEmpty
     if (n_boxes_total > 0 && args.L.max_boxes > 0) {
         const dim3 cgrid((unsigned)args.in.n_samples, (unsigned)((args.L.max_boxes + 3) / 4));  // a warp per box, one grid column per sample
         fused_cullids_kernel<<<cgrid, 128, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
         ++X->last_launches;
     }
-    if (fov) MSC_CUDA(cudaStreamWaitEvent(stream, X->join, 0));  // the class tables are ready
+    if (forked) MSC_CUDA(cudaStreamWaitEvent(stream, X->join, 0));  // the class tables are ready
     return MSC_OK;
 }
 
@@ -497,7 +516,6 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     X->last_fastdiv = fast ? 1 : 0;
     X->last_config = gen3 ? 9 : 7;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-    MSC_CUDA(cudaMemsetAsync(ws + T.counter_off, 0, 256, stream));
     // fine edge classes for the kInnerMax x kInnerMax BEV cells around the sensor, where several image-column rays cross a 2 m cull cell
     int inner = fov ? (params->bev_res < kInnerMax ? params->bev_res : kInnerMax) : 0;
     inner &= ~1;
@@ -525,7 +543,6 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
         const size_t ncell = (size_t)params->bev_res * (size_t)params->bev_res;
         MSC_CUDA(cudaMemsetAsync(out->bev_ci, 0, (size_t)in->n_samples * ncell * 8, stream));
         MSC_CUDA(cudaMemsetAsync(out->bev_height, 0, (size_t)in->n_samples * ncell * 4, stream));
-        MSC_CUDA(cudaMemsetAsync(ws + T.splitstats_off, 0, (size_t)in->n_samples * MSC_STATS_STRIDE * 4, stream));
     }
     const long long items = (long long)in->n_samples * args.split;
     const int grid = (int)(items < X->sms ? items : X->sms);

@@ -41,10 +41,15 @@ class DeviceBatch:
     tensors: Dict[str, torch.Tensor]
 
     def struct(self) -> MscBatchIn:
-        t = self.tensors
-        hb = self.host
-        hint = int(hb.sweep_count.sum() // max(hb.n_samples, 1)) if hb.sweep_count.size else 0
-        return MscBatchIn(hb.n_samples, hb.max_boxes_per_sample, hb.n_boxes, min(hint, 2 ** 31 - 1), *[t[k].data_ptr() for k in _IN_FIELDS])
+        """The C struct of this batch (built once: the tensors of a DeviceBatch never move)."""
+        st = self.__dict__.get("_struct")
+        if st is None or self.__dict__.get("_struct_host") is not self.host:
+            t = self.tensors
+            hb = self.host
+            hint = int(hb.sweep_count.sum() // max(hb.n_samples, 1)) if hb.sweep_count.size else 0
+            st = MscBatchIn(hb.n_samples, hb.max_boxes_per_sample, hb.n_boxes, min(hint, 2 ** 31 - 1), *[t[k].data_ptr() for k in _IN_FIELDS])
+            self.__dict__["_struct"], self.__dict__["_struct_host"] = st, hb
+        return st
 
 
 @dataclass
@@ -66,6 +71,12 @@ class BatchResult:
     table_arena: Optional[torch.Tensor] = None   # the six small tables above are views into this one buffer (one copy / one collective)
 
     def struct(self) -> MscBatchOut:
+        st = self.__dict__.get("_struct")
+        if st is None:
+            st = self.__dict__["_struct"] = self._make_struct()
+        return st
+
+    def _make_struct(self) -> MscBatchOut:
         return MscBatchOut(self.box_count.data_ptr(), self.box_nearest.data_ptr(), self.box_centroid.data_ptr(),
                            self.proj_visible.data_ptr(), self.proj_extent.data_ptr(), self.bev_ci.data_ptr(), self.bev_height.data_ptr(),
                            self.stats.data_ptr())
@@ -150,6 +161,8 @@ class GeometryEngine:
         _capi.check(self.lib.msc_device_info(C.byref(sm), C.byref(smem), C.byref(maj), C.byref(mnr)), "msc_device_info")
         self.sm_count, self.smem_optin, self.cc = sm.value, smem.value, (maj.value, mnr.value)
         self._workspaces: Dict[int, torch.Tensor] = {}  # one work counter per stream (kernels on different streams overlap)
+        self._ws_need: Dict[tuple, int] = {}
+        self._params_cache: Dict[tuple, tuple] = {}
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ transfers
@@ -236,10 +249,17 @@ class GeometryEngine:
             raise _capi.MscError(f"params.n_cams={p.n_cams} but the batch was packed for {db.host.n_cams} cameras")
         if out is None:
             out = self.alloc_result(db.host, p)
-        mp, bi, bo = make_params(p), db.struct(), out.struct()
+        key = tuple(p.__dict__.values())  # GeomParams is mutable: the cache is keyed by value
+        mp = self._params_cache.get(key)
+        if mp is None:
+            mp = self._params_cache[key] = make_params(p)
+        bi, bo = db.struct(), out.struct()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        need = int(self.lib.msc_fused_workspace_bytes(self.ctx.handle, C.byref(mp), db.host.n_samples, db.host.n_boxes))
+        wkey = (db.host.n_samples, db.host.n_boxes, p.bev_res, p.bev_range, self.ctx.get_option("cull_shift"))
         ws = self._workspaces.get(stream)
+        if self._ws_need.get(wkey) is None:
+            self._ws_need[wkey] = int(self.lib.msc_fused_workspace_bytes(self.ctx.handle, C.byref(mp), db.host.n_samples, db.host.n_boxes))
+        need = self._ws_need[wkey]
         if ws is None or ws.numel() < need:
             ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
         _capi.check(self.lib.msc_fused_evidence_batch(self.ctx.handle, C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),

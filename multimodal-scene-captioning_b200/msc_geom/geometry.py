@@ -7,6 +7,8 @@ Restates the pose algebra of nuscenes-devkit (un-vendored dependency of the refe
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 
@@ -76,6 +78,7 @@ def ref_from_sweep(ref_ego_pose7, ref_calib7, sweep_ego_pose7, sweep_calib7) -> 
     return np.ascontiguousarray(M[:3, :4])
 
 
+@functools.lru_cache(maxsize=64)
 def sqrt_thresholds(lo: float, hi: float):
     """Smallest float32 s with sqrt(s) > lo and largest float32 s with sqrt(s) < hi (float32 sqrt).
 

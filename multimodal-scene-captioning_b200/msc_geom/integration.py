@@ -14,12 +14,17 @@ from . import lidar_agent as _la
 from . import scenegraph_agent as _sg
 from .engine import GeometryEngine
 
-_LIDAR_METHODS = ("_preprocess_point_cloud", "_segment_ground", "_generate_multi_layer_bev", "_generate_cluster_visualization")
+# local-geometry methods swapped in; `_classify_batch_with_llm`, `call_llm` and everything else remote stay the reference's own
+_LIDAR_METHODS = ("_preprocess_point_cloud", "_segment_ground", "_generate_multi_layer_bev", "_generate_cluster_visualization",
+                  "_cluster_visualizations", "_cluster_metadata", "_detect_objects_3d")
 _SCENE_METHODS = ("_parse_annotations", "_build_spatial_zones")
 
 
-def patch_reference(lidar_cls=None, scenegraph_cls=None, engine: Optional[GeometryEngine] = None):
-    """Monkey-patch the reference classes in place.  Returns the engine the patched methods use."""
+def patch_reference(lidar_cls=None, scenegraph_cls=None, engine: Optional[GeometryEngine] = None, camera_cls=None):
+    """Monkey-patch the reference classes in place.  Returns the engine the patched methods use.
+    LiDARAgent: filter / split / BEV, and `_detect_objects_3d` (device DBSCAN + all cluster views in one launch), which hands each batch
+    of ten to the reference's OWN `_classify_batch_with_llm(cluster_images, cluster_metadata)`.  SceneGraphAgent: the annotation table.
+    CameraAgent: `process` gains the additive `sample` argument whose box -> camera evidence is merged into `context`."""
     eng = engine or GeometryEngine()
 
     def _ensure(self):
@@ -39,6 +44,16 @@ def patch_reference(lidar_cls=None, scenegraph_cls=None, engine: Optional[Geomet
         lidar_cls._params = _la.LiDARAgent._params
         for name in _LIDAR_METHODS:
             setattr(lidar_cls, name, _wrap(getattr(_la.LiDARAgent, name)))
+    if camera_cls is not None:
+        from .camera_agent import evidence_context
+        ref_process = camera_cls.process
+
+        def process(self, images, camera_names, context=None, sample=None):
+            if sample is not None:
+                context = {**(context or {}), **evidence_context(eng, sample)}
+            return ref_process(self, images, camera_names, context)
+        process.__doc__ = ref_process.__doc__
+        camera_cls.process = process
     if scenegraph_cls is not None:
         scenegraph_cls._table = _wrap(_sg.SceneGraphAgent._table)
         for name in _SCENE_METHODS:

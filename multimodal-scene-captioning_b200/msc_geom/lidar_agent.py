@@ -110,14 +110,13 @@ def cluster_mosaic(images: List[np.ndarray]) -> np.ndarray:
 
 class LiDARAgent:
     def __init__(self, client, model: str, agent_name: str, engine: Optional[GeometryEngine] = None,
-                 llm: Optional[Callable[..., str]] = None, cluster_classifier: Optional[Callable[[List[dict]], List[dict]]] = None):
+                 llm: Optional[Callable[..., str]] = None, cluster_classifier: Optional[Callable[..., List[dict]]] = None):
         self.client, self.model, self.agent_name = client, model, agent_name
         self.dbscan_eps = 0.5          # lidar_agent.py:44
         self.dbscan_min_samples = 10   # :45
         self.bev_resolution = 800      # :48
         self.bev_range = 50            # :49
         self.engine = engine or GeometryEngine()
-        self.dbscan_backend = "cuda"  # "sklearn" restores the reference's CPU call; labels are identical either way
         self.llm = llm
         self.cluster_classifier = cluster_classifier
 
@@ -167,33 +166,37 @@ class LiDARAgent:
         return meta
 
     def _detect_objects_3d(self, object_points: np.ndarray) -> List[DetectedObject]:
+        """lidar_agent.py:134-239 with the local work on the device: DBSCAN (scikit-learn's labelling), per-cluster boxes, and the
+        4-view images of ALL clusters in one launch; the classifier sees what the reference's sees -- per batch of ten, the cluster
+        images and their metadata (`_classify_batch_with_llm(cluster_images, cluster_metadata)`, :358)."""
         if len(object_points) < self.dbscan_min_samples:
             return []
-        if self.dbscan_backend == "sklearn":
-            from sklearn.cluster import DBSCAN
-            labels = DBSCAN(eps=self.dbscan_eps, min_samples=self.dbscan_min_samples).fit(object_points[:, :3]).labels_
-        else:
-            labels = ops.dbscan(self.engine, object_points, self.dbscan_eps, self.dbscan_min_samples)
+        labels = ops.dbscan(self.engine, object_points, self.dbscan_eps, self.dbscan_min_samples)
         uniq = set(labels)
         uniq.discard(-1)
         order = [int(l) for l in uniq if int((labels == l).sum()) >= 5]  # set-iteration order, like lidar_agent.py:154-165
         if not order:
             return []
-        meta = self._cluster_metadata(object_points, labels.astype(np.int32), order)
+        labels = labels.astype(np.int32)
+        meta = self._cluster_metadata(object_points, labels, order)
+        images = self._cluster_visualizations(object_points, labels, order)
         out: List[DetectedObject] = []
         for start in range(0, len(meta), 10):  # the reference classifies in batches of 10 (:189)
             batch = meta[start:start + 10]
-            cls = self._classify_batch(batch)
+            cls = self._classify_batch_with_llm(images[start:start + 10], batch)
             for m, c in zip(batch, cls):
                 if c["category"] != "unknown" and c["confidence"] > 0.3:
                     out.append(DetectedObject(c["category"], m["center"], m["dimensions"], m["num_points"], m["distance"], m["direction"],
                                               c["confidence"]))
         return out
 
-    def _classify_batch(self, batch: List[dict]) -> List[dict]:
+    def _classify_batch_with_llm(self, cluster_images: List[np.ndarray], cluster_metadata: List[dict]) -> List[dict]:
+        """The remote half of lidar_agent.py:358-504, injected: `cluster_classifier(images, mosaic, metadata)` gets the batch's cluster
+        images, the mosaic the reference would send (:366-386) and the metadata.  Without one every cluster takes the reference's
+        parse-failure default (:503)."""
         if self.cluster_classifier is None:
-            return [{"category": "unknown", "confidence": 0.5} for _ in batch]  # the reference's parse-failure default (:503)
-        return self.cluster_classifier(batch)
+            return [{"category": "unknown", "confidence": 0.5} for _ in cluster_metadata]
+        return self.cluster_classifier(cluster_images, cluster_mosaic(cluster_images), cluster_metadata)
 
     # ------------------------------------------------------------------ evidence -> features / report (host, tiny)
     def _extract_semantic_features(self, detected_objects: List[DetectedObject], ground_points: np.ndarray, object_points: np.ndarray) -> Dict[str, Any]:

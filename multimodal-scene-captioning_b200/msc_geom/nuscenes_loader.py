@@ -83,11 +83,13 @@ class SyntheticNuScenesLoader:
 class NuScenesLoader:
     """Real-data loader: the reference's keys (nuscenes_loader.py:88-101) plus the additive multi-sweep keys."""
 
-    def __init__(self, dataroot: str, version: str = "v1.0-mini", n_sweeps: int = 10):
+    def __init__(self, dataroot: str, version: str = "v1.0-mini", n_sweeps: int = 10, lazy_sweeps: bool = False):
+        """lazy_sweeps: sweeps carry the .pcd.bin `path` instead of `points_raw` (and `point_cloud` / `images` are left out), so
+        msc_geom.io.stage_batch reads the files straight into one pinned batch buffer -- the on-disk step of the batched path."""
         if not NUSCENES_AVAILABLE:
             raise ImportError("nuscenes-devkit is required. Install with: pip install nuscenes-devkit")
         from pathlib import Path
-        self.dataroot, self.version, self.n_sweeps = Path(dataroot), version, n_sweeps
+        self.dataroot, self.version, self.n_sweeps, self.lazy_sweeps = Path(dataroot), version, n_sweeps, lazy_sweeps
         self.nusc = NuScenes(version=version, dataroot=str(dataroot), verbose=True)
         self.camera_channels = list(CAMERA_CHANNELS)
 
@@ -105,7 +107,8 @@ class NuScenesLoader:
         for ch in self.camera_channels:
             if ch in sample["data"]:
                 sd = nusc.get("sample_data", sample["data"][ch])
-                images.append(np.array(Image.open(self.dataroot / sd["filename"])))
+                if not self.lazy_sweeps:
+                    images.append(np.array(Image.open(self.dataroot / sd["filename"])))
                 names.append(sd["channel"])
                 cs = nusc.get("calibrated_sensor", sd["calibrated_sensor_token"])
                 cameras.append({"channel": ch, "ego_pose": self._pose7(nusc.get("ego_pose", sd["ego_pose_token"])), "calib": self._pose7(cs),
@@ -115,10 +118,11 @@ class NuScenesLoader:
         ref_cal = self._pose7(nusc.get("calibrated_sensor", ref_sd["calibrated_sensor_token"]))
         sweeps, sd = [], ref_sd
         for _ in range(self.n_sweeps):  # App. A.1: walk `prev` from the keyframe
-            raw = np.fromfile(str(self.dataroot / sd["filename"]), dtype=np.float32).reshape(-1, 5)
             pose = self._pose7(nusc.get("ego_pose", sd["ego_pose_token"]))
             cal = self._pose7(nusc.get("calibrated_sensor", sd["calibrated_sensor_token"]))
-            sweeps.append({"points_raw": raw, "ref_from_sensor": ref_from_sweep(ref_pose, ref_cal, pose, cal), "ego_pose": pose, "calib": cal,
+            data = ({"path": str(self.dataroot / sd["filename"])} if self.lazy_sweeps
+                    else {"points_raw": np.fromfile(str(self.dataroot / sd["filename"]), dtype=np.float32).reshape(-1, 5)})
+            sweeps.append({**data, "ref_from_sensor": ref_from_sweep(ref_pose, ref_cal, pose, cal), "ego_pose": pose, "calib": cal,
                            "time_lag": 1e-6 * (ref_sd["timestamp"] - sd["timestamp"])})
             if sd["prev"] == "":
                 break
@@ -133,7 +137,8 @@ class NuScenesLoader:
                                 "num_lidar_pts": ann["num_lidar_pts"], "num_radar_pts": ann["num_radar_pts"]})
         scene = nusc.get("scene", sample["scene_token"])
         return {"sample_token": sample_token, "timestamp": sample["timestamp"], "scene_description": scene["description"], "scene_name": scene["name"],
-                "images": images, "camera_names": names, "point_cloud": sweeps[0]["points_raw"][:, :4], "annotations": annotations,
+                "images": images, "camera_names": names, "point_cloud": None if self.lazy_sweeps else sweeps[0]["points_raw"][:, :4],
+                "annotations": annotations,
                 "metadata": {"location": nusc.get("log", scene["log_token"])["location"], "nbr_objects": len(annotations)},
                 "lidar_sweeps": sweeps, "ego_pose": ref_pose, "lidar_calib": ref_cal, "cameras": cameras}
 

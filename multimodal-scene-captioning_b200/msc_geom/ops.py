@@ -242,6 +242,8 @@ def dbscan(eng: GeometryEngine, xyz: np.ndarray, eps: float = 0.5, min_samples: 
     n = int(rows.shape[0])
     if n == 0:
         return np.zeros(0, np.int64)
+    if not np.isfinite(rows[:, :3]).all():  # scikit-learn's check_array raises on NaN / inf input too
+        raise ValueError("Input X contains NaN or infinity (DBSCAN needs finite coordinates, like sklearn.cluster.DBSCAN.fit).")
     lo = rows[:, :3].min(axis=0).astype(np.float64)
     hi = rows[:, :3].max(axis=0).astype(np.float64)
     cell = float(eps) * (1.0 + 1e-6)  # a hair above eps so float rounding can never put neighbours two cells apart

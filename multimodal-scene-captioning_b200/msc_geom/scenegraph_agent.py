@@ -43,6 +43,7 @@ class SceneGraphAgent:
                               "left_close": (0, 10, "left"), "left_medium": (10, 30, "left"), "right_close": (0, 10, "right"),
                               "right_medium": (10, 30, "right"), "back_close": (0, 10, "back"), "back_medium": (10, 30, "back")}
         self._last_table: Optional[Dict[str, np.ndarray]] = None
+        self.scene_graph_fn = None  # the remote half: user prompt -> scene-graph dict (None: the reference's local fallback graph)
 
     def _table(self, annotations: List[Dict]) -> Dict[str, np.ndarray]:
         n = len(annotations)
@@ -112,11 +113,71 @@ class SceneGraphAgent:
         objs = self._parse_annotations(annotations)
         return serialize.scene_graph_user_prompt(self._categorize_objects(objs), self._build_spatial_zones(objs), annotations, context)
 
+    # ------------------------------------------------------------------ entry point (scenegraph_agent.py:148-178)
     def process(self, annotations: List[Dict], context: Optional[Dict] = None) -> Dict[str, Any]:
+        """Same keys as the reference: `agent`, `modality`, `scene_graph` (the dict form of its HierarchicalSceneGraph), `observations`
+        (its text summary).  The graph itself is the reference's LLM half: `scene_graph_fn(user_prompt) -> dict` supplies it when
+        injected; without one, or when it raises, the graph is the reference's own local fallback (:379-421).  The GPU-computed
+        evidence rides along under the additive `evidence` key."""
         objs = self._parse_annotations(annotations)
         cats = self._categorize_objects(objs)
         zones = self._build_spatial_zones(objs)
-        return {"agent": self.agent_name, "modality": "scene_graph",
+        graph = self._generate_scene_graph(cats, zones, annotations, context)
+        return {"agent": self.agent_name, "modality": "scene_graph", "scene_graph": graph, "observations": self._generate_summary(graph),
                 "evidence": {"objects": objs, "categorized": {k: [o["id"] for o in v] for k, v in cats.items()},
-                             "spatial_zones": {k: [o["id"] for o in v] for k, v in zones.items()}},
-                "observations": ""}
+                             "spatial_zones": {k: [o["id"] for o in v] for k, v in zones.items()}}}
+
+    def _generate_scene_graph(self, categorized: Dict, spatial_zones: Dict, annotations: List[Dict], context: Optional[Dict]) -> Dict[str, Any]:
+        fn = getattr(self, "scene_graph_fn", None)
+        if fn is not None:
+            try:
+                return dict(fn(serialize.scene_graph_user_prompt(categorized, spatial_zones, annotations, context)))
+            except Exception as e:  # noqa: BLE001 -- the reference catches everything here and falls back (:378-380)
+                print(f"  \u26a0\ufe0f  Error generating scene graph: {e}")
+        return fallback_scene_graph(len(annotations))
+
+    def _generate_summary(self, scene_graph: Dict[str, Any]) -> str:
+        """Text summary of a scene-graph dict, line for line the reference's (:423-490)."""
+        graph = scene_graph
+        env, road, lanes = graph["environment"], graph["road_structure"], graph["road_structure"]["lanes"]
+        lines = ["=== Hierarchical Scene Graph ===\n", f"Scene: {graph['scene_summary']}", f"Total objects: {graph['total_objects']}\n",
+                 "Environment:", f"  - Lighting: {env['lighting']}", f"  - Weather: {env['weather']}", f"  - Location: {env['location_type']}\n",
+                 "Road Structure:", f"  - Type: {road['road_type']}", f"  - Lanes: {lanes['lane_count']} {lanes['lane_type']} lanes",
+                 f"  - Ego position: {lanes['ego_lane_position']} lane"]
+        if road["road_elements"]:
+            lines.append(f"  - Elements: {len(road['road_elements'])} road signs/markings\n")
+        tp = graph["traffic_participants"]
+        lines += ["Traffic Participants:", f"  - Vehicles: {len(tp['vehicles'])}", f"  - Cyclists: {len(tp['cyclists'])}",
+                  f"  - Vulnerable road users: {len(tp['vulnerable_road_users'])}\n"]
+        sw = graph["sidewalk_areas"]
+        if sw["has_sidewalk"]:
+            lines += [f"Sidewalk Areas ({sw['location']}):", f"  - Pedestrians: {len(sw['pedestrians'])}", f"  - Static objects: {len(sw['static_objects'])}\n"]
+        infra = graph["static_infrastructure"]
+        if sum(len(infra[k]) for k in ("barriers", "traffic_cones", "construction", "other")) > 0:
+            lines.append("Static Infrastructure:")
+            if infra["barriers"]:
+                lines.append(f"  - Barriers: {len(infra['barriers'])}")
+            if infra["traffic_cones"]:
+                lines.append(f"  - Traffic cones: {len(infra['traffic_cones'])}")
+            if infra["construction"]:
+                lines.append(f"  - Construction: {len(infra['construction'])}\n")
+        if graph["spatial_zones"]:
+            lines.append("Spatial Zones:")
+            lines += [f"  - {z['zone_name']}: {len(z['objects'])} objects (criticality: {z['criticality']})" for z in graph["spatial_zones"] if z["objects"]]
+        if graph["safety_critical_elements"]:
+            lines.append("\nSafety Critical Elements:")
+            lines += [f"  - {e}" for e in graph["safety_critical_elements"]]
+        return "\n".join(lines)
+
+
+def fallback_scene_graph(total_objects: int) -> Dict[str, Any]:
+    """`model_dump()` of the minimal graph the reference returns when its LLM call fails (scenegraph_agent.py:381-421)."""
+    unknown = "unknown"
+    return {"scene_summary": "Error generating scene graph",
+            "environment": {"lighting": unknown, "weather": unknown, "visibility_overall": unknown, "location_type": unknown},
+            "road_structure": {"road_type": unknown, "lanes": {"lane_count": 0, "lane_type": unknown, "ego_lane_position": unknown, "lane_markings": []},
+                               "road_elements": [], "surface_condition": unknown},
+            "traffic_participants": {"vehicles": [], "cyclists": [], "vulnerable_road_users": []},
+            "sidewalk_areas": {"has_sidewalk": False, "pedestrians": [], "static_objects": [], "location": unknown},
+            "static_infrastructure": {"barriers": [], "traffic_cones": [], "construction": [], "other": []},
+            "spatial_zones": [], "safety_critical_elements": ["Scene graph generation failed"], "total_objects": int(total_objects)}

@@ -63,6 +63,16 @@ def image_to_base64(img: np.ndarray) -> str:
     return base64.b64encode(buf.getvalue()).decode()
 
 
+def jpeg_base64(img: np.ndarray) -> str:
+    """camera_agent.py:128-137: uint8 conversion, JPEG quality 85 through Pillow (no channel swap: camera images are RGB), base64."""
+    from PIL import Image
+    if img.dtype != np.uint8:
+        img = (img * 255).astype(np.uint8)
+    buf = BytesIO()
+    Image.fromarray(img).save(buf, format="JPEG", quality=85)
+    return base64.b64encode(buf.getvalue()).decode()
+
+
 def ext_evidence(annotations: Sequence[Dict], box_count: np.ndarray, box_nearest: np.ndarray, box_centroid: np.ndarray,
                  proj_visible: np.ndarray, camera_names: Sequence[str], relations: Optional[Dict[str, Any]] = None,
                  max_pairs: int = 20) -> Dict[str, Any]:

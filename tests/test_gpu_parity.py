@@ -301,7 +301,7 @@ def test_lidar_agent_process_matches_reference(engine, golden_dir, golden_json):
     np.random.seed(0)
     sample = create_loader(None, use_mock=True).get_sample_by_scene_index(0, 0)
     agent = LiDARAgent(object(), "m", "LiDARAgent", engine=engine, llm=lambda *a, **k: "STUB",
-                       cluster_classifier=lambda batch: [{"category": "car", "confidence": 0.9} for _ in batch])
+                       cluster_classifier=lambda images, mosaic, batch: [{"category": "car", "confidence": 0.9} for _ in batch])
     out = agent.process(sample["point_cloud"])
     ref = golden_json["process_mock"]
     assert out["bev_metadata"] == ref["bev_metadata"] and out["structured_report"] == ref["structured_report"]
@@ -310,6 +310,48 @@ def test_lidar_agent_process_matches_reference(engine, golden_dir, golden_json):
     rf = dict(ref["semantic_features"]); rd = rf.pop("nearest_object_distance")
     assert sf == rf and ((near is None and rd is None) or float(near.distance) == rd)
     assert json.loads(json.dumps(out["detected_objects"])) == ref["detected_objects"]
+
+
+def test_detect_objects_hands_cluster_images_to_the_classifier(engine, golden_dir):
+    """lidar_agent.py:198-224: the classifier gets, per batch of ten, the clusters' 4-view images (here rastered in ONE launch for all
+    clusters) and their metadata; the images equal the per-cluster method's and the mosaic is the reference's batch sheet."""
+    from msc_geom.lidar_agent import LiDARAgent, cluster_mosaic
+    g = np.load(os.path.join(golden_dir, "clusters_synth.npz"))
+    seen = []
+
+    def classifier(images, mosaic, meta):
+        seen.append((images, mosaic, meta))
+        return [{"category": "car", "confidence": 0.9} for _ in meta]
+    agent = LiDARAgent(object(), "m", "n", engine=engine, cluster_classifier=classifier)
+    objs = agent._detect_objects_3d(g["object"])
+    n = len(g["num_points"])
+    assert len(objs) == n and sum(len(b[2]) for b in seen) == n and all(len(b[0]) == len(b[2]) <= 10 for b in seen)
+    assert [m["index"] for b in seen for m in b[2]] == list(range(n))
+    labels = g["labels"]
+    order = [int(l) for l in set(labels.tolist()) if l != -1 and (labels == l).sum() >= 5]
+    first = agent._generate_cluster_visualization(g["object"][labels == order[0]])
+    assert seen[0][0][0].shape == (512, 512, 3) and np.array_equal(seen[0][0][0], first)
+    assert np.array_equal(seen[0][1], cluster_mosaic(seen[0][0]))
+
+
+def test_scenegraph_process_returns_the_reference_keys(engine, golden_dir):
+    from msc_geom.scenegraph_agent import SceneGraphAgent
+    gold = json.load(open(os.path.join(golden_dir, "agent_golden.json")))
+    anns = gold["scenegraph_fallback"]["annotations"]
+    agent = SceneGraphAgent(object(), "m", "SceneGraphAgent", engine=engine)
+    out, ref = agent.process(anns), gold["scenegraph_fallback"]["result"]
+    assert {k: out[k] for k in ref} == ref                               # agent, modality, scene_graph (local fallback), observations
+    assert [o["id"] for o in out["evidence"]["objects"]] == ["obj_0", "obj_1"]   # additive key: the GPU-computed table
+    full = gold["scenegraph_llm"]["result"]
+    prompts = []
+    agent.scene_graph_fn = lambda prompt: (prompts.append(prompt), full["scene_graph"])[1]   # the injected LLM half
+    out2 = agent.process(anns)
+    assert {k: out2[k] for k in full} == full and prompts[0] == agent.scene_graph_prompt(anns)
+
+    def failing(prompt):
+        raise RuntimeError("LLM down")
+    agent.scene_graph_fn = failing
+    assert agent.process(anns)["scene_graph"] == ref["scene_graph"]      # the reference's except-branch (:378-421)
 
 
 def test_cluster_metadata_matches_reference(engine, golden_dir):
@@ -323,6 +365,22 @@ def test_cluster_metadata_matches_reference(engine, golden_dir):
     for i, m in enumerate(meta):
         assert np.array_equal(m["center"], g["center"][i]) and np.array_equal(m["dimensions"], g["dimensions"][i])
         assert m["distance"] == g["distance"][i] and m["num_points"] == g["num_points"][i] and m["direction"] == str(g["direction"][i])
+
+
+def test_dbscan_rejects_non_finite_and_merges_long_chains(engine):
+    """NaN / inf input raises like scikit-learn's check_array; a long chain of core points (the worst case for hooking) is one cluster."""
+    from sklearn.cluster import DBSCAN
+    X = np.random.default_rng(1).normal(0, 1, (50, 3))
+    X[7, 1] = np.nan
+    with pytest.raises(ValueError):
+        ops.dbscan(engine, X)
+    X[7, 1] = np.inf
+    with pytest.raises(ValueError):
+        ops.dbscan(engine, X)
+    t = np.arange(6000, dtype=np.float64) * 0.04            # a 240 m line, every point a core point, one component
+    chain = np.stack([t, 0.01 * np.sin(t), np.zeros_like(t)], 1)
+    got = ops.dbscan(engine, chain, 0.5, 10)
+    assert np.array_equal(got, DBSCAN(eps=0.5, min_samples=10).fit(chain).labels_) and got.max() == 0
 
 
 def _dbscan_cases():
