@@ -16,22 +16,6 @@ namespace msc {
 // wedges, and the per-cull-cell wedge classes.  The streaming kernel then only copies its sample's rows to smem.
 
 
-// Per-edge classes of one cell against one wedge: bit0 = the wedge may contain points of the cell,
-// bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same extremes over the cell and the same guard band
-// as classify_cell(); an edge every point of the cell passes needs no exact test, an edge every point fails empties the wedge.
-__device__ __forceinline__ uint32_t classify_cell_edges(const float* __restrict__ wq, float x0, float x1, float y0, float y1) {
-    // both cross products are affine in (x, y): over the rectangle they range over (value at the centre) -/+ (extent), which costs a
-    // third of four corner evaluations.  The float evaluation error of the exact test is < 1e-4 for |p| < 128 m and << guard for |p|
-    // up to the 1200 m "absorbing" edge cells, far inside the 2e-3 guard band.
-    const float guard = 2e-3f;
-    const float hx = 0.5f * (x1 - x0), hy = 0.5f * (y1 - y0);
-    const float qx = 0.5f * (x0 + x1) - wq[0], qy = 0.5f * (y0 + y1) - wq[1];
-    const float cr = wq[4] * qy - wq[5] * qx, cr_e = fabsf(wq[4]) * hy + fabsf(wq[5]) * hx;
-    const float cl = qx * wq[3] - qy * wq[2], cl_e = fabsf(wq[3]) * hx + fabsf(wq[2]) * hy;
-    if (cr + cr_e < -guard || cl + cl_e < -guard) return 0u;  // outside
-    return 1u | ((cr - cr_e > guard) ? 0u : 2u) | ((cl - cl_e > guard) ? 0u : 4u);
-}
-
 // camera wedge: apex = camera centre in the sensor xy-plane, edges = image columns 0 and W (f64, no FMA)
 __device__ void compute_wedge(int image_w, const double* __restrict__ lcal, const double* __restrict__ ccal, const double* __restrict__ K,
                               float* __restrict__ wq) {
@@ -129,48 +113,6 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
     }
 }
 
-// Edge classes per (sample, cull cell) and per (sample, fine cell = one BEV cell of the inner_dim x inner_dim square around the sensor),
-// from the wedges the table kernel wrote (launched after it).  Class word: bit c = camera c's wedge may contain points of the cell,
-// bit 8 + c = its right edge is undecided inside the cell, bit 16 + c = its left edge is.  A block stages its sample's wedges in smem.
-__global__ void __launch_bounds__(256) fused_fovcls_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
-    const msc_params& P = A.P;
-    const int n_cams = P.n_cams;
-    const int ncc = A.L.cull_dim * A.L.cull_dim;
-    const int n_inner = A.L.inner_dim * A.L.inner_dim;
-    const int per_sample = ncc + n_inner;
-    const int sample = blockIdx.y;
-    __shared__ float wq[MSC_MAX_CAMS * 6];
-    if (threadIdx.x < MSC_MAX_CAMS * 6) wq[threadIdx.x] = reinterpret_cast<const float*>(ws + T.wedge_off)[(size_t)sample * MSC_MAX_CAMS * 6 + threadIdx.x];
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per_sample) return;
-    const float big = 4.0f * P.bev_range + 1000.0f, pad = 2e-3f;
-    float x0, x1, y0, y1;
-    uint32_t* dst;
-    if (i >= ncc) {  // one BEV cell: every point whose bev_cell() index is (ix, iy) lies in the padded square
-        const int j = i - ncc, jy = j / A.L.inner_dim, jx = j - jy * A.L.inner_dim;
-        const float cell_b = A.two_r / A.resf;
-        const int ix = A.L.inner_lo + jx, iy = A.L.inner_lo + jy, last_b = P.bev_res - 1;  // first / last BEV cells absorb what is clipped into them
-        x0 = (ix == 0) ? -big : (-P.bev_range + (float)ix * cell_b - pad); x1 = (ix == last_b) ? big : (-P.bev_range + (float)(ix + 1) * cell_b + pad);
-        y0 = (iy == 0) ? -big : (-P.bev_range + (float)iy * cell_b - pad); y1 = (iy == last_b) ? big : (-P.bev_range + (float)(iy + 1) * cell_b + pad);
-        dst = reinterpret_cast<uint32_t*>(ws + T.innercls_off) + (size_t)sample * n_inner + j;
-    } else {
-        const int gy = i / A.L.cull_dim, gx = i - gy * A.L.cull_dim;
-        const float cell_m = (A.two_r / A.resf) * (float)(1 << A.L.cull_shift);
-        const int last = A.L.cull_dim - 1;
-        // edge cells absorb everything clipped into them
-        x0 = (gx == 0) ? -big : (-P.bev_range + (float)gx * cell_m - pad); x1 = (gx == last) ? big : (-P.bev_range + (float)(gx + 1) * cell_m + pad);
-        y0 = (gy == 0) ? -big : (-P.bev_range + (float)gy * cell_m - pad); y1 = (gy == last) ? big : (-P.bev_range + (float)(gy + 1) * cell_m + pad);
-        dst = reinterpret_cast<uint32_t*>(ws + T.edgecls_off) + (size_t)sample * ncc + i;
-    }
-    uint32_t eb = 0;
-    for (int c = 0; c < n_cams; ++c) {
-        const uint32_t k = classify_cell_edges(wq + c * 6, x0, x1, y0, y1);
-        eb |= ((k & 1u) << c) | (((k >> 1) & 1u) << (8 + c)) | (((k >> 2) & 1u) << (16 + c));  // in-bit, right / left edge undecided
-    }
-    *dst = eb;
-}
-
 // Candidate-box ids per (sample, cull cell): conservative oriented rasterisation of every box footprint, one warp per box (lanes
 // share the cells of its bounding rectangle), into a workspace table the host pre-fills with kCullEmpty.
 __global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
@@ -193,7 +135,7 @@ __global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTimeRing = 64;
 
-// One context per caller (host thread / engine): options, the side stream of the class kernel, the timing ring and the facts about the
+// One context per caller (host thread / engine): options, the timing ring and the facts about the
 // most recent call live here, not in process globals, so contexts on different host threads, streams or devices never share state.
 struct msc_fused_ctx {
     int device = 0, sms = 0, smem_optin = 0;
@@ -207,9 +149,6 @@ struct msc_fused_ctx {
     int opt_time_kernel = 0;   // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
     int last_window = 0, last_smem = 0, last_fastdiv = 0, last_tile_pts = 0, last_threads = 0, last_launches = 0, last_split = 1, last_grid = 0,
         last_config = 0;
-    bool side_made = false;
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
     bool ev_made = false;
     cudaEvent_t ev0[kTimeRing], ev1[kTimeRing];
     long long ev_count = 0;  // calls timed so far
@@ -261,8 +200,6 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes,
     T.counter_off = off; off = align(off + 256);
     T.boxprep_off = off; off = align(off + nb * kBoxStride * 4);
     T.wedge_off = off; off = align(off + ns * MSC_MAX_CAMS * 6 * 4);
-    T.edgecls_off = off; off = align(off + ns * dim * dim * 4);
-    T.innercls_off = off; off = align(off + ns * kInnerMax * kInnerMax * 4);
     T.cullids_off = off; off = align(off + ns * dim * dim * 4);
     T.boxscr_off = off; off = align(off + nb * 32);
     T.splitstats_off = off; off = align(off + ns * MSC_STATS_STRIDE * 4);
@@ -301,56 +238,22 @@ static int compute_layout(const msc_fused_ctx* X, const msc_params& P, int max_b
     return 0;
 }
 
-static int side_stream(msc_fused_ctx* X) {
-    if (!X->side_made) {
-        MSC_CUDA(cudaStreamCreateWithFlags(&X->side, cudaStreamNonBlocking));
-        MSC_CUDA(cudaEventCreateWithFlags(&X->fork, cudaEventDisableTiming));
-        MSC_CUDA(cudaEventCreateWithFlags(&X->join, cudaEventDisableTiming));
-        X->side_made = true;
-    }
-    return MSC_OK;
-}
-
-// tables (prepared boxes, projection, wedges -> workspace), then the class kernel on the context's side stream beside the cull-id kernel
-// (both only need the table kernel's output); the caller's stream waits for the class tables before its streaming kernel
-static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, bool fov,
-                         cudaStream_t stream) {
-    const int ncc = args.L.cull_dim * args.L.cull_dim;
+// tables (prepared boxes, projection, wedges, housekeeping -> workspace), then the candidate-box ids of every cull cell; the per-cell
+// edge classes of the camera wedges are computed by the streaming kernels themselves, per sample, from the wedges
+static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, cudaStream_t stream) {
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
     if ((long long)args.in.n_samples * cams > work) work = (long long)args.in.n_samples * cams;
     X->last_launches = 0;
-    if (work > 0) {
-        fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
-        MSC_CUDA(cudaGetLastError());
-        ++X->last_launches;
-    }
-    // the class kernel runs beside the cull-id kernel on the context's side stream when the batch is big enough for that to pay for the
-    // fork / join events; small batches (latency) keep one stream
-    const bool forked = fov && args.in.n_samples >= 32;
-    if (fov) {
-        cudaStream_t cs = stream;
-        if (forked) {
-            int rc = side_stream(X);
-            if (rc != MSC_OK) return rc;
-            MSC_CUDA(cudaEventRecord(X->fork, stream));
-            MSC_CUDA(cudaStreamWaitEvent(X->side, X->fork, 0));
-            cs = X->side;
-        }
-        const int per_sample = ncc + args.L.inner_dim * args.L.inner_dim;
-        const dim3 fgrid((unsigned)((per_sample + 255) / 256), (unsigned)args.in.n_samples);
-        fused_fovcls_kernel<<<fgrid, 256, 0, cs>>>(args, T, ws);
-        MSC_CUDA(cudaGetLastError());
-        if (forked) MSC_CUDA(cudaEventRecord(X->join, X->side));
-        ++X->last_launches;
-    }
+    fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
+    MSC_CUDA(cudaGetLastError());
+    ++X->last_launches;
     if (n_boxes_total > 0 && args.L.max_boxes > 0) {
         const dim3 cgrid((unsigned)args.in.n_samples, (unsigned)((args.L.max_boxes + 3) / 4));  // a warp per box, one grid column per sample
         fused_cullids_kernel<<<cgrid, 128, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
         ++X->last_launches;
     }
-    if (forked) MSC_CUDA(cudaStreamWaitEvent(stream, X->join, 0));  // the class tables are ready
     return MSC_OK;
 }
 
@@ -400,7 +303,6 @@ int msc_fused_create(msc_fused_ctx** out) {
 
 int msc_fused_destroy(msc_fused_ctx* X) {
     if (!X) return MSC_OK;
-    if (X->side_made) { cudaStreamDestroy(X->side); cudaEventDestroy(X->fork); cudaEventDestroy(X->join); }
     if (X->ev_made)
         for (int i = 0; i < kTimeRing; ++i) { cudaEventDestroy(X->ev0[i]); cudaEventDestroy(X->ev1[i]); }
     delete X;
@@ -538,7 +440,7 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     X->last_smem = args.L.total_bytes;
     args.split = split;
     X->last_split = args.split;
-    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, fov, stream)) != MSC_OK) return rc;
+    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, stream)) != MSC_OK) return rc;
     if (args.split > 1) {  // parts merge into the output layers and the scratch with reductions: zero them first
         const size_t ncell = (size_t)params->bev_res * (size_t)params->bev_res;
         MSC_CUDA(cudaMemsetAsync(out->bev_ci, 0, (size_t)in->n_samples * ncell * 8, stream));

@@ -49,6 +49,7 @@ struct StreamMisc {  // small per-CTA state at misc_off
     int* h32;                           // read back by the few lanes per warp that update the periphery
     double pose[kStreamPoseSmem * 12];  // this sample's 3x4 sweep transforms
     double wpose[kMaxWarps * 12];       // per-warp slot for sweeps beyond kStreamPoseSmem
+    float wq[MSC_MAX_CAMS * 6];         // this sample's camera wedges (fused_tables_kernel), source of the per-cell edge classes
 };
 
 int stream_misc_bytes() { return (int)sizeof(StreamMisc); }
@@ -82,9 +83,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
     uint32_t* const work_counter = reinterpret_cast<uint32_t*>(ws + T.counter_off);
     const float* const g_boxprep = reinterpret_cast<const float*>(ws + T.boxprep_off);
     const float* const g_wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
-    const uint32_t* const g_edgecls = reinterpret_cast<const uint32_t*>(ws + T.edgecls_off);
     const uint32_t* const g_cullids = reinterpret_cast<const uint32_t*>(ws + T.cullids_off);
-    const uint32_t* const g_innercls = reinterpret_cast<const uint32_t*>(ws + T.innercls_off);
 
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform as far as the compiler is concerned
@@ -128,6 +127,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
         }
         for (int i = tid; i < min(n_sw, kStreamPoseSmem) * 12; i += NT) misc->pose[i] = A.in.sweep_pose[(size_t)sw0 * 12 + i];
         if (tid < MSC_STATS_STRIDE) misc->stats[tid] = 0u;
+        if (FOV && tid < MSC_MAX_CAMS * 6) misc->wq[tid] = g_wedges[(size_t)sample * MSC_MAX_CAMS * 6 + tid];
         if (tid == 0) {
             misc->ci64 = reinterpret_cast<unsigned long long*>(A.out.bev_ci) + (size_t)sample * ncell;
             misc->h32 = reinterpret_cast<int*>(A.out.bev_height) + (size_t)sample * ncell;
@@ -176,13 +176,13 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
             const int n_w4 = (L.win_w * L.win_w * 8) / 16;
             for (int i = tid; i < n_w4; i += NT) w4[i] = make_uint4(0, 0, 0, 0);
             const int n_cull = L.cull_dim * L.cull_dim;
-            const uint32_t* ec = g_edgecls + (size_t)sample * n_cull;
             const uint32_t* ids = g_cullids + (size_t)sample * n_cull;  // candidate boxes per cull cell (fused_cullids_kernel)
-            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(ids[i], (FOV && n_cams > 0) ? ec[i] : 0u);
-            if (FOV) {  // fine edge classes of the BEV cells around the sensor
+            // edge classes of the sample's camera wedges per cull cell, and per BEV cell around the sensor (fine table)
+            for (int i = tid; i < n_cull; i += NT) cull[i] = make_uint2(ids[i], (FOV && n_cams > 0) ? edge_class_word(A, misc->wq, i) : 0u);
+            if (FOV) {
                 const int n_inner = L.inner_dim * L.inner_dim;
                 uint32_t* inner = reinterpret_cast<uint32_t*>(smem + L.inner_off);
-                for (int i = tid; i < n_inner; i += NT) inner[i] = g_innercls[(size_t)sample * n_inner + i];
+                for (int i = tid; i < n_inner; i += NT) inner[i] = edge_class_word(A, misc->wq, n_cull + i);
             }
             for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
             const float4* bsrc = reinterpret_cast<const float4*>(g_boxprep + (size_t)bx0 * kBoxStride);

@@ -39,6 +39,7 @@ struct S3Misc {  // small per-CTA state at misc_off
     int* h32;                         // the few lanes per warp that update cells outside the window / the height layer
     double pose[kS3PoseSmem * 12];    // this sample's 3x4 sweep transforms
     double wpose[kS3Warps * 12];      // per-warp slot for sweeps beyond kS3PoseSmem
+    float wq[MSC_MAX_CAMS * 6];       // this sample's camera wedges (fused_tables_kernel), source of the per-cell edge classes
 };
 
 int stream3_misc_bytes() { return (int)sizeof(S3Misc); }
@@ -92,9 +93,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) stream3_kernel(const __grid_con
     uint32_t* const work_counter = reinterpret_cast<uint32_t*>(ws + T.counter_off);
     const float* const g_boxprep = reinterpret_cast<const float*>(ws + T.boxprep_off);
     const float* const g_wedges = reinterpret_cast<const float*>(ws + T.wedge_off);
-    const uint32_t* const g_edgecls = reinterpret_cast<const uint32_t*>(ws + T.edgecls_off);
     const uint32_t* const g_cullids = reinterpret_cast<const uint32_t*>(ws + T.cullids_off);
-    const uint32_t* const g_innercls = reinterpret_cast<const uint32_t*>(ws + T.innercls_off);
 
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform as far as the compiler is concerned
@@ -148,6 +147,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) stream3_kernel(const __grid_con
         }
         for (int i = tid; i < min(n_sw, kS3PoseSmem) * 12; i += NT) misc->pose[i] = A.in.sweep_pose[(size_t)sw0 * 12 + i];
         if (tid < MSC_STATS_STRIDE) misc->stats[tid] = 0u;
+        if (FOV && tid < MSC_MAX_CAMS * 6) misc->wq[tid] = g_wedges[(size_t)sample * MSC_MAX_CAMS * 6 + tid];
         if (tid == 0) {
             misc->ci64 = reinterpret_cast<unsigned long long*>(A.out.bev_ci) + (size_t)sample * ncell;
             misc->h32 = reinterpret_cast<int*>(A.out.bev_height) + (size_t)sample * ncell;
@@ -205,15 +205,13 @@ __global__ void __launch_bounds__(kS3Threads, 1) stream3_kernel(const __grid_con
         };
         {
             const uint32_t* ids = g_cullids + (size_t)sample * n_cull;       // candidate boxes per cull cell (fused_cullids_kernel)
-            const uint32_t* const ec = g_edgecls + (size_t)sample * n_cull;   // coarse classes (one per cull cell)
+            // edge classes of the sample's camera wedges per cull cell, and per BEV cell around the sensor (fine table)
             for (int i = tid; i < n_cull; i += NT) {
-                const uint32_t cls = FOV ? ec[i] : 0u;
+                const uint32_t cls = FOV ? edge_class_word(A, misc->wq, i) : 0u;
                 cull[i] = make_uint2(ids[i], cls | (s3_code_of(cls) << kCodeShift));
             }
-            if (FOV) {
-                const uint32_t* const ic = g_innercls + (size_t)sample * n_inner;
-                for (int i = tid; i < n_inner; i += NT) inner[i] = ic[i];
-            }
+            if (FOV)
+                for (int i = tid; i < n_inner; i += NT) inner[i] = edge_class_word(A, misc->wq, n_cull + i);
             if (tid < 32) { wsinkc[tid] = 0u; wsinkc[32 + n_win + tid] = 0u; }
             for (int i = tid; i < n_win; i += NT) wisum[i] = 0u;
             for (int i = tid; i < n_boxes * kAccWords; i += NT) boxacc[i] = ((i % kAccWords) == 1) ? 0x7f800000u : 0u;
