@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the short measurements of BASELINE configs 2, 4 and 5")
     ap.add_argument("--fov", type=int, default=1)
     ap.add_argument("--window", type=int, default=0)
-    ap.add_argument("--config", type=int, default=0, help="streaming kernel: 0 = auto, 9 = stream3.cu, 7 = fused_stream.cu")
-    ap.add_argument("--split", type=int, default=0, help="CTAs per sample (0 = auto)")
+    ap.add_argument("--config", type=int, default=0, help="streaming kernel: 0 = auto, 10 = stream4.cu, 7 = fused_stream.cu")
+    ap.add_argument("--grid", type=int, default=0, help="stream4.cu: CTAs of the launch (0 = auto)")
+    ap.add_argument("--ppt", type=int, default=0, help="stream4.cu: points per lane, 2 or 4 (0 = the library's default)")
     ap.add_argument("--cull-shift", type=int, default=-1)
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")
     return ap.parse_args()
@@ -191,7 +192,9 @@ def main():
     _capi.set_option("window", args.window)
     _capi.set_option("config", args.config)
     _capi.set_option("cull_shift", args.cull_shift)
-    _capi.set_option("split", args.split)
+    _capi.set_option("grid", args.grid)
+    if args.ppt:
+        _capi.set_option("ppt", args.ppt)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -281,7 +284,7 @@ def main():
         m = {"workload": wname_, "scaling": "strong" if strong else "weak", "total_samples": total, "samples_this_rank": S,
              "value": total * steps / (elapsed_ms * 1e-3), "unit": UNIT, "ms_per_step": elapsed_ms / steps, "steps": steps,
              "call_ms": call_ms, "kernel_ms": (sum(own) / len(own)) if own else call_ms, "gpu_launches": eng.kernel_launches - launches0,
-             "kernel_config": _capi.get_option("last_config"), "ctas_per_sample": _capi.get_option("last_split"),
+             "kernel_config": _capi.get_option("last_config"),
              "grid": _capi.get_option("last_grid"), "bev_window_cells": _capi.get_option("last_window"),
              "tile_pts": _capi.get_option("tile_pts"), "threads": _capi.get_option("threads"), "table_arena_bytes": arena_bytes,
              "points_per_step_this_rank": hb.n_points, "algorithmic_bytes": algorithmic_bytes(hb, params), "n_unique": n_unique, "reps": reps}
@@ -406,7 +409,7 @@ def main():
                        "points_per_step_per_gpu": main["points_per_step_this_rank"],
                        "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (main["points_per_step_this_rank"] * 20 / 1e9),
                        "fov_counts": bool(args.fov), "bev_window_cells": main["bev_window_cells"], "tile_pts": main["tile_pts"],
-                       "threads": main["threads"], "kernel_config": main["kernel_config"], "ctas_per_sample": main["ctas_per_sample"],
+                       "threads": main["threads"], "kernel_config": main["kernel_config"], "grid": main["grid"],
                        "table_gather": "one all_gather_into_tensor of the table arena per step on a side stream (double-buffered)" if world > 1 else "none (1 GPU)",
                        "table_arena_bytes": main["table_arena_bytes"]},
             "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,

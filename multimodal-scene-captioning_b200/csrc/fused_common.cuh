@@ -1,5 +1,5 @@
 // fused_common.cuh -- types and device helpers shared by the table kernels (fused_evidence.cu) and the two streaming kernels
-// (stream3.cu: config 9, the default; fused_stream.cu: config 7, the previous generation, which still serves fov_keep_mask != 0).
+// (stream4.cu: config 10, the default; fused_stream.cu: config 7, the TMA-ring generation, which also serves fov_keep_mask != 0).
 #pragma once
 #include "msc_common.cuh"
 
@@ -20,6 +20,7 @@ struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
     int32_t cull_dim, cull_shift;  // cull cell = BEV cell >> cull_shift
     int32_t inner_off, inner_dim, inner_lo;  // fused_stream.cu: edge classes per BEV cell for cells [inner_lo, inner_lo + inner_dim)^2 (0: none)
     int32_t max_boxes;             // capacity of the smem box tables
+    int32_t pcnt_off, isum_delta;  // stream4.cu: bytes from the window region's start to the cull-cell count words / from array A to array B
 };
 
 struct FusedArgs {
@@ -30,7 +31,7 @@ struct FusedArgs {
     // host-precomputed scalars (exact): 2r, res, RN(1/2r), 2^centroid_shift, 2^intensity_shift
     float two_r, resf, rcp_two_r, cscale, iscale;
     int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
-    int32_t split;          // stream3.cu: CTAs that share one sample (1 = a sample per CTA)
+    int32_t split;          // (unused since stream3.cu was retired: always 1)
 };
 
 // BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein
@@ -97,7 +98,8 @@ __device__ __forceinline__ void bev_cell_xy(float x, float y, float r, float two
 
 struct TableLayout {  // offsets (bytes) into the workspace
     size_t counter_off, boxprep_off, wedge_off, cullids_off;
-    size_t boxscr_off, splitstats_off;  // stream3.cu, split > 1: per-box (count | min << 32, 3 biased sums) u64 x 4, per-sample stats + ticket
+    size_t boxscr_off, splitstats_off;  // merge scratch of samples processed in parts: per-box (count | min << 32, 3 biased sums) u64 x 4, per-sample stats + ticket
+    size_t tileoff_off;                 // stream4.cu: [n_samples + 1] exclusive prefix of warp tiles per sample
     size_t total;
 };
 
@@ -105,11 +107,14 @@ struct TableLayout {  // offsets (bytes) into the workspace
 int stream_misc_bytes();
 void stream_shape_info(int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
 int launch_stream_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream);
-// stream3.cu (config 9)
-int stream3_misc_bytes();
-int stream3_ring_bytes();
-int stream3_queue_bytes();
-int launch_stream3_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream);
+// stream4.cu (config 10)
+int stream4_misc_bytes();
+int stream4_queue_bytes(int ppt);
+int stream4_threads(int ppt);
+int stream4_window_extra(int n_cull);
+void stream4_finish_layout(FusedLayout* L);
+int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, cudaStream_t stream, int* launches);
+int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, cudaStream_t stream);
 
 // Per-edge classes of one cell against one wedge: bit0 = the wedge may contain points of the cell,
 // bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same extremes over the cell and the same guard band
@@ -162,7 +167,7 @@ __device__ __forceinline__ uint32_t edge_class_word(const FusedArgs& A, const fl
 __device__ __forceinline__ bool in_wedge(const float* __restrict__ wq, float x, float y) {
     const float qx = __fsub_rn(x, wq[0]), qy = __fsub_rn(y, wq[1]);
     const float cr = __fmaf_rn(wq[4], qy, -__fmul_rn(wq[5], qx));
-    const float cl = __fmaf_rn(qx, wq[3], -__fmul_rn(qy, wq[2]));
+    const float cl = __fmaf_rn(-wq[2], qy, __fmul_rn(wq[3], qx));  // same shape as cr: product on the x term, fma on the y term
     return (cr >= 0.0f) && (cl >= 0.0f);
 }
 

@@ -1,6 +1,6 @@
 // fused_evidence.cu -- host side of the fused hot path (msc_fused_* entry points) and its three table kernels.
 //
-// The hot path is one pass over the raw sweeps of a batch of samples (stream3.cu; fused_stream.cu for fov_keep_mask != 0).
+// The hot path is one pass over the raw sweeps of a batch of samples (stream4.cu; fused_stream.cu for fov_keep_mask != 0).
 // Everything that does not touch points runs once per batch in small, fully parallel kernels and lands in the workspace:
 // prepared boxes (devkit points_in_box vectors, App. A.2), box -> camera projection (A.3), camera wedges, the per-cell
 // edge classes of the wedges, and the candidate-box ids of every cull cell.  Semantics: SURVEY.md App. A.
@@ -49,18 +49,14 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     float* const boxprep = reinterpret_cast<float*>(ws + T.boxprep_off);
     float* const wedges = reinterpret_cast<float*>(ws + T.wedge_off);
-    // (0) housekeeping that would otherwise be three memsets: the streaming kernel's work counter, the candidate-id table
-    // (kCullEmpty everywhere; fused_cullids_kernel inserts into it after this kernel) and the merge scratch of split samples
+    // (0) housekeeping that would otherwise be two memsets: the streaming kernel's work counter and the candidate-id table
+    // (kCullEmpty everywhere; fused_cullids_kernel inserts into it after this kernel)
     {
         const size_t nthreads = (size_t)gridDim.x * blockDim.x;
         if (gid == 0) *reinterpret_cast<uint32_t*>(ws + T.counter_off) = 0u;
         uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off);
         const size_t n_ids = (size_t)A.in.n_samples * (size_t)(A.L.cull_dim * A.L.cull_dim);
         for (size_t i = gid; i < n_ids; i += nthreads) ids[i] = kCullEmpty;
-        if (A.split > 1) {
-            uint32_t* st = reinterpret_cast<uint32_t*>(ws + T.splitstats_off);
-            for (size_t i = gid; i < (size_t)A.in.n_samples * MSC_STATS_STRIDE; i += nthreads) st[i] = 0u;
-        }
     }
     // sample of a global box index: binary search in sample_box_off
     auto sample_of_box = [&](int gb) {
@@ -92,10 +88,6 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
         o[14] = __fmaf_rn(o[11], o[11], __fmaf_rn(o[10], o[10], __fmul_rn(o[9], o[9])));
         o[15] = 0.0f;
         o[16] = (float)c[0]; o[17] = (float)c[1]; o[18] = (float)c[2]; o[19] = 0.0f;  // centre, for the cull rasterisation
-        if (A.split > 1) {  // merge scratch of a split sample: count 0 | min +inf, three biased sums
-            unsigned long long* scr = reinterpret_cast<unsigned long long*>(ws + T.boxscr_off) + (size_t)gid * 4;
-            scr[0] = 0x7f800000ull << 32; scr[1] = 0ull; scr[2] = 0ull; scr[3] = 0ull;
-        }
     }
     // (2) box -> camera projection (App. A.3): one thread per (box, camera)
     if (n_cams > 0 && gid < n_boxes_total * n_cams) {
@@ -143,12 +135,12 @@ struct msc_fused_ctx {
     int opt_window = 0;        // 0 = auto (largest that fits)
     int opt_cull_shift = -1;   // -1 = auto (cull cell ~ 2 m)
     int opt_fastdiv = 1;       // allow the Markstein division for whitelisted divisors
-    int opt_config = 0;        // 0 = auto: stream3.cu when the batch is split over CTAs, else fused_stream.cu; 9 / 7 force one of them
+    int opt_config = 0;        // 0 = auto (by how evenly whole samples fill the SMs); 10 / 7 force stream4.cu / fused_stream.cu
                                // (fov_keep_mask != 0 always takes fused_stream.cu)
-    int opt_split = 0;         // CTAs per sample: 0 = auto from n_samples / SM count, else forced (stream3.cu only)
+    int opt_grid = 0;          // stream4.cu: CTAs of the launch, 0 = auto (the SM count, fewer for batches of a few thousand rows)
+    int opt_ppt = 2;           // stream4.cu: points per lane, 2 (768 threads) or 4 (512 threads)
     int opt_time_kernel = 0;   // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
-    int last_window = 0, last_smem = 0, last_fastdiv = 0, last_tile_pts = 0, last_threads = 0, last_launches = 0, last_split = 1, last_grid = 0,
-        last_config = 0;
+    int last_window = 0, last_smem = 0, last_fastdiv = 0, last_tile_pts = 0, last_threads = 0, last_launches = 0, last_grid = 0, last_config = 0;
     bool ev_made = false;
     cudaEvent_t ev0[kTimeRing], ev1[kTimeRing];
     long long ev_count = 0;  // calls timed so far
@@ -203,12 +195,13 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes,
     T.cullids_off = off; off = align(off + ns * dim * dim * 4);
     T.boxscr_off = off; off = align(off + nb * 32);
     T.splitstats_off = off; off = align(off + ns * MSC_STATS_STRIDE * 4);
+    T.tileoff_off = off; off = align(off + (ns + 1) * 4);
     T.total = off;
     return T;
 }
 
 // shared-memory layout of either streaming kernel.  window_cell_bytes / window_extra: bytes per window cell and fixed bytes next to the
-// window (stream3.cu: two arrays + their sink words); inner_dim > 0 reserves a fine class table in smem (fused_stream.cu).
+// window (stream4.cu: two arrays + their sink and cull-cell words); inner_dim > 0 reserves a fine class table in smem.
 static int compute_layout(const msc_fused_ctx* X, const msc_params& P, int max_boxes_in_batch, int ring_bytes, int queue_bytes, int misc_bytes,
                           int inner_dim, bool inner_in_smem, int window_extra, FusedLayout* L) {
     const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
@@ -255,24 +248,6 @@ static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLay
         ++X->last_launches;
     }
     return MSC_OK;
-}
-
-// CTAs per sample for stream3.cu when the batch has fewer samples than the device has SMs: the split that minimises
-// rounds x (1 / split + overhead), where `overhead` is the per-part prologue + merge cost relative to one whole sample.
-static int auto_split(int n_samples, int sms, int points_hint) {
-    if (n_samples <= 0 || n_samples >= sms) return 1;
-    const double pts = points_hint > 0 ? (double)points_hint : 347200.0;
-    const double overhead = 20000.0 / pts;  // ~ the time of 20 k points
-    const int max_split = (int)(pts / (64.0 * 32.0)) < 1 ? 1 : ((int)(pts / (64.0 * 32.0)) > 32 ? 32 : (int)(pts / (64.0 * 32.0)));
-    int best = 1;
-    double best_cost = 1e30;
-    for (int s = 1; s <= max_split; ++s) {
-        const long long items = (long long)n_samples * s;
-        const double rounds = (double)((items + sms - 1) / sms);
-        const double cost = rounds * (1.0 / s + (s > 1 ? overhead : 0.0));
-        if (cost < best_cost - 1e-12) { best_cost = cost; best = s; }
-    }
-    return best;
 }
 
 }  // namespace msc
@@ -324,8 +299,9 @@ int msc_fused_set_option(msc_fused_ctx* X, const char* key, int32_t value) {
     if (!strcmp(key, "window")) { X->opt_window = value; return MSC_OK; }
     if (!strcmp(key, "cull_shift")) { X->opt_cull_shift = value; return MSC_OK; }
     if (!strcmp(key, "fastdiv")) { X->opt_fastdiv = value ? 1 : 0; return MSC_OK; }
-    if (!strcmp(key, "config")) { MSC_REQUIRE(value == 0 || value == 7 || value == 9, "config must be 0 (auto), 9 (stream3.cu) or 7 (fused_stream.cu)"); X->opt_config = value; return MSC_OK; }
-    if (!strcmp(key, "split")) { MSC_REQUIRE(value >= 0 && value <= 64, "split out of range"); X->opt_split = value; return MSC_OK; }
+    if (!strcmp(key, "config")) { MSC_REQUIRE(value == 0 || value == 7 || value == 10, "config must be 0 (auto), 10 (stream4.cu) or 7 (fused_stream.cu)"); X->opt_config = value; return MSC_OK; }
+    if (!strcmp(key, "grid")) { MSC_REQUIRE(value >= 0 && value <= 4096, "grid out of range"); X->opt_grid = value; return MSC_OK; }
+    if (!strcmp(key, "ppt")) { MSC_REQUIRE(value == 2 || value == 4, "ppt must be 2 or 4"); X->opt_ppt = value; return MSC_OK; }
     if (!strcmp(key, "time_kernel")) { X->opt_time_kernel = value ? 1 : 0; return MSC_OK; }
     set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
@@ -340,12 +316,12 @@ int msc_fused_get_option(msc_fused_ctx* X, const char* key, int32_t* value) {
     if (!strcmp(key, "cull_shift")) { *value = X->opt_cull_shift; return MSC_OK; }
     if (!strcmp(key, "fastdiv")) { *value = X->opt_fastdiv; return MSC_OK; }
     if (!strcmp(key, "config")) { *value = X->opt_config; return MSC_OK; }
-    if (!strcmp(key, "split")) { *value = X->opt_split; return MSC_OK; }
+    if (!strcmp(key, "grid")) { *value = X->opt_grid; return MSC_OK; }
+    if (!strcmp(key, "ppt")) { *value = X->opt_ppt; return MSC_OK; }
     if (!strcmp(key, "time_kernel")) { *value = X->opt_time_kernel; return MSC_OK; }
     if (!strcmp(key, "last_window")) { *value = X->last_window; return MSC_OK; }
     if (!strcmp(key, "last_smem")) { *value = X->last_smem; return MSC_OK; }
     if (!strcmp(key, "last_fastdiv")) { *value = X->last_fastdiv; return MSC_OK; }
-    if (!strcmp(key, "last_split")) { *value = X->last_split; return MSC_OK; }
     if (!strcmp(key, "last_grid")) { *value = X->last_grid; return MSC_OK; }
     if (!strcmp(key, "last_config")) { *value = X->last_config; return MSC_OK; }
     if (!strcmp(key, "tile_pts")) { *value = X->last_tile_pts; return MSC_OK; }
@@ -408,24 +384,30 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     args.split = 1;
     const bool fov = X->opt_fov != 0 && params->n_cams > 0;
     const bool fast = X->opt_fastdiv != 0 && fastdiv_verified(args.two_r);
-    // Kernel choice.  fused_stream.cu: one sample per CTA, the faster of the two on batches that fill the device (and the only one with the
-    // per-point wedge classes a FOV *filter* needs).  stream3.cu: a sample can be split over CTAs -- batches smaller than the SM count.
+    // Kernel choice.  stream4.cu: rows read straight into registers, static partition of the batch in warp tiles (any batch size fills the
+    // device evenly).  fused_stream.cu: the TMA-ring generation, one sample per CTA at a time -- the only one with the per-point wedge
+    // classes a FOV *filter* (fov_keep_mask) needs.
     const bool keepmask = fov && params->fov_keep_mask != 0u;
-    int split = 1;
-    if (!keepmask && X->opt_config != 7) split = X->opt_split > 0 ? X->opt_split : auto_split(in->n_samples, X->sms, in->points_per_sample_hint);
-    const bool gen3 = !keepmask && (X->opt_config == 9 || (X->opt_config == 0 && split > 1));
-    if (!gen3) split = 1;
+    int gen = keepmask ? 7 : X->opt_config;
+    if (gen == 0) {
+        // auto: fused_stream.cu hands out whole samples, so its last round of a batch leaves SMs idle; it is ~10 % faster per point (its
+        // TMA ring keeps the raw rows off the LSU data pipe, the unit both kernels saturate first) -- stream4.cu wins whenever the
+        // sample count is not close to a multiple of the SM count (a shard of a few dozen samples, a single keyframe, 404 samples ...)
+        const long long rounds = ((long long)in->n_samples + X->sms - 1) / X->sms;
+        const double fill = (double)in->n_samples / (double)(rounds * X->sms);
+        gen = fill >= 0.88 ? 7 : 10;
+    }
     X->last_fastdiv = fast ? 1 : 0;
-    X->last_config = gen3 ? 9 : 7;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     // fine edge classes for the kInnerMax x kInnerMax BEV cells around the sensor, where several image-column rays cross a 2 m cull cell
     int inner = fov ? (params->bev_res < kInnerMax ? params->bev_res : kInnerMax) : 0;
     inner &= ~1;
-    int rc;
-    if (gen3) {
-        rc = compute_layout(X, *params, in->max_boxes_per_sample, stream3_ring_bytes(), stream3_queue_bytes(), stream3_misc_bytes(), inner, true, 256,
-                            &args.L);
-        X->last_tile_pts = 64; X->last_threads = 1024;
+    int rc = -1;
+    if (gen == 10) {
+        rc = compute_layout(X, *params, in->max_boxes_per_sample, 0, stream4_queue_bytes(X->opt_ppt), stream4_misc_bytes(), inner, true,
+                            stream4_window_extra(cdim * cdim), &args.L);
+        if (rc == 0) stream4_finish_layout(&args.L);
+        X->last_tile_pts = 32 * X->opt_ppt; X->last_threads = stream4_threads(X->opt_ppt);
     } else {
         int threads = 0, tile_pts = 0, ring = 0, queue = 0;
         stream_shape_info(&threads, &tile_pts, &ring, &queue);
@@ -436,21 +418,25 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
         set_error("shared-memory layout does not fit (%d bytes available)", X->smem_optin);
         return MSC_ERR_UNSUPPORTED;
     }
+    X->last_config = gen;
     X->last_window = args.L.win_w;
     X->last_smem = args.L.total_bytes;
-    args.split = split;
-    X->last_split = args.split;
     if ((rc = launch_tables(X, args, T, ws, in->n_boxes, stream)) != MSC_OK) return rc;
-    if (args.split > 1) {  // parts merge into the output layers and the scratch with reductions: zero them first
-        const size_t ncell = (size_t)params->bev_res * (size_t)params->bev_res;
-        MSC_CUDA(cudaMemsetAsync(out->bev_ci, 0, (size_t)in->n_samples * ncell * 8, stream));
-        MSC_CUDA(cudaMemsetAsync(out->bev_height, 0, (size_t)in->n_samples * ncell * 4, stream));
+    int grid;
+    if (gen == 10) {
+        // every CTA gets the same number of warp tiles; a batch of a few thousand rows is not spread thinner than one tile per warp
+        const long long pts = in->points_per_sample_hint > 0 ? in->points_per_sample_hint : 347200;
+        const int tile_pts = 32 * X->opt_ppt, warps = stream4_threads(X->opt_ppt) / 32;
+        const long long est_tiles = (long long)in->n_samples * ((pts + tile_pts - 1) / tile_pts);
+        long long g = X->opt_grid > 0 ? X->opt_grid : est_tiles / warps;
+        grid = (int)(g < 1 ? 1 : (g > X->sms ? X->sms : g));
+        if ((rc = launch_stream4_partition(args, T, ws, grid, X->opt_ppt, stream, &X->last_launches)) != MSC_OK) return rc;
+    } else {
+        grid = in->n_samples < X->sms ? in->n_samples : X->sms;
     }
-    const long long items = (long long)in->n_samples * args.split;
-    const int grid = (int)(items < X->sms ? items : X->sms);
     X->last_grid = grid;
     if ((rc = time_begin(X, stream)) != MSC_OK) return rc;
-    rc = gen3 ? launch_stream3_kernel(args, T, ws, grid, fov, fast, stream) : launch_stream_kernel(args, T, ws, grid, fov, fast, stream);
+    rc = gen == 10 ? launch_stream4_kernel(args, T, ws, grid, X->opt_ppt, fov, fast, stream) : launch_stream_kernel(args, T, ws, grid, fov, fast, stream);
     if (rc != MSC_OK) return rc;
     ++X->last_launches;
     return time_end(X, stream);

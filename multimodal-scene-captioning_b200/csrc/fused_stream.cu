@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                 float4 E = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (c < n_cams) {
                     const float* wq = g_wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6;
-                    // right edge: fma(w4, qy, -(w5 * qx)) >= 0; left edge: fma(w3, qx, -(w2 * qy)) >= 0  (in_wedge)
-                    E = (tid >= MSC_MAX_CAMS) ? make_float4(wq[0], wq[1], wq[3], wq[2]) : make_float4(wq[0], wq[1], wq[4], wq[5]);
+                    // cr = fma(A, qy, -(B * qx)) >= 0 with (A, B) = (w4, w5) for the right edge, (-w2, -w3) for the left one  (in_wedge)
+                    E = (tid >= MSC_MAX_CAMS) ? make_float4(wq[0], wq[1], -wq[2], -wq[3]) : make_float4(wq[0], wq[1], wq[4], wq[5]);
                 }
                 misc->edge[tid] = E;
                 if (tid == 0) misc->edge_pad = E;
@@ -371,9 +371,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) stream_evidence_kernel(const _
                     st[u] = sbits ^ low;
                     const float4 E = lds128(edge_s + (uint32_t)(e * 16));
                     const float qx = __fsub_rn(xr[u], E.x), qy = __fsub_rn(yr[u], E.y);
-                    const bool left = e >= MSC_MAX_CAMS;
-                    const float sv = left ? qx : qy, tv = left ? qy : qx;
-                    const float cr = __fmaf_rn(E.z, sv, -__fmul_rn(E.w, tv));
+                    const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
                     if (!(cr >= 0.0f)) pass[u] &= ~low;
                 };
 #pragma unroll

@@ -173,7 +173,7 @@ void orc_cam_wedge(const double lidar_calib[7], const double cam_calib[7], const
 static inline int in_wedge(const float w[6], float x, float y) {
     float qx = x - w[0], qy = y - w[1];
     float c_r = fmaf(w[4], qy, -(w[5] * qx)); /* cross(e_right, q) */
-    float c_l = fmaf(qx, w[3], -(qy * w[2])); /* cross(q, e_left)  */
+    float c_l = fmaf(-w[2], qy, w[3] * qx);   /* cross(q, e_left): same shape as c_r -- product on the x term, fma on the y term */
     return (c_r >= 0.0f) && (c_l >= 0.0f);
 }
 

@@ -18,7 +18,7 @@ from tests import oracle_bridge as OB
 IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
 
 
-DEFAULT_CONFIGS = _capi.FUSED_CONFIGS  # 9: stream3.cu (default), 7: fused_stream.cu (previous generation)
+DEFAULT_CONFIGS = _capi.FUSED_CONFIGS  # 10: stream4.cu (default), 7: fused_stream.cu (the TMA-ring generation)
 
 
 def check_fused(eng, samples, params=None, config=None, n_cams=6):
@@ -49,7 +49,7 @@ def check_fused(eng, samples, params=None, config=None, n_cams=6):
     return hb, got
 
 
-@pytest.mark.parametrize("config", [9, 7])
+@pytest.mark.parametrize("config", [10, 7])
 def test_fused_config3_shape(engine, config):
     check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
 
@@ -199,31 +199,39 @@ def test_fused_fov_counts_off_and_small_window(engine):
     _capi.set_option("window", 0)
 
 
-def test_fused_samples_split_over_ctas(engine):
-    """stream3.cu splits a batch smaller than the SM count over several CTAs per sample (parts merge integer accumulators with global
-    reductions, the last ticket finalises): results must not depend on the split -- forced splits, the automatic one, one keyframe."""
-    import torch
+def test_fused_static_partition_over_ctas(engine):
+    """stream4.cu partitions a batch statically in warp tiles: CTA b of G owns global tiles [b T / G, (b + 1) T / G), so samples
+    straddle CTA boundaries and merge their parts with integer reductions (the last ticket finalises).  Results must not depend on
+    G -- forced grids from one CTA to more CTAs than tiles, the automatic one, one keyframe, empty samples at either end."""
     s = [make_sample(80 + i, n_sweeps=1 + 4 * (i % 3), n_boxes=15 + 40 * i) for i in range(3)]
     s.append({"point_cloud": np.random.default_rng(6).normal(0, 12, (3000, 4)).astype(np.float32), "annotations": []})
+    empty = make_sample(32, n_sweeps=1, n_boxes=3)
+    empty["lidar_sweeps"] = [dict(empty["lidar_sweeps"][0], points_raw=empty["lidar_sweeps"][0]["points_raw"][:0])]
     try:
-        for split in (1, 2, 5, 16, 0):
-            _capi.set_option("split", split)
-            check_fused(engine, s, config=9)
-            assert _capi.get_option("last_config") == 9
-            assert _capi.get_option("last_split") == split or split == 0
-        assert _capi.get_option("last_split") > 1                       # 4 samples on 148 SMs: the automatic choice splits
-        check_fused(engine, [make_sample(90, n_sweeps=1, n_boxes=60)], config=9)   # BASELINE config 2: one keyframe
+        for ppt in (4, 2):  # both launch shapes: 512 threads x 4 points per lane, 768 x 2
+            _capi.set_option("ppt", ppt)
+            for grid in (1, 2, 3, 7, 37, 148, 0):
+                _capi.set_option("grid", grid)
+                check_fused(engine, s, config=10)
+                assert _capi.get_option("last_config") == 10 and _capi.get_option("threads") == (512 if ppt == 4 else 768)
+                assert _capi.get_option("last_grid") == grid or grid == 0
+        check_fused(engine, [make_sample(90, n_sweeps=1, n_boxes=60)], config=10)   # BASELINE config 2: one keyframe
         assert _capi.get_option("last_grid") > 1
-        _capi.set_option("window", 20)                                    # most cells through the global reductions, split as well
-        _capi.set_option("split", 7)
-        check_fused(engine, s, config=9)
+        for grid in (1, 5, 148):
+            _capi.set_option("grid", grid)
+            check_fused(engine, [empty, s[0], empty, empty, s[3], empty], config=10)
+            check_fused(engine, [empty, empty], config=10)
+        _capi.set_option("window", 20)                                    # most cells through the global reductions, partitioned as well
+        _capi.set_option("grid", 11)
+        check_fused(engine, s, config=10)
     finally:
-        _capi.set_option("split", 0)
+        _capi.set_option("grid", 0)
+        _capi.set_option("ppt", _capi.DEFAULT_FUSED_PPT)
         _capi.set_option("window", 0)
         _capi.set_option("config", _capi.DEFAULT_FUSED_CONFIG)
 
 
-@pytest.mark.parametrize("config", [9, 7])
+@pytest.mark.parametrize("config", [10, 7])
 def test_fused_full_size_batch_properties(engine, config):
     """BASELINE config-3 batch at the benchmark's size (592 samples, 205.5 M points): size-independent properties, replica
     equality (bit-reproducibility under different scheduling), idempotence, and the oracle on sampled samples."""

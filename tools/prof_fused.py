@@ -10,8 +10,9 @@ from msc_geom import _capi
 n_unique = int(os.environ.get("PROF_UNIQUE", "4")); reps = int(os.environ.get("PROF_REPS", "37")); launches = int(os.environ.get("PROF_LAUNCHES", "3"))
 eng = GeometryEngine()
 _capi.set_option("fov", int(os.environ.get("PROF_FOV", "1")))
-_capi.set_option("split", int(os.environ.get("PROF_SPLIT", "0")))
-_capi.set_option("config", int(os.environ.get("PROF_CONFIG", "9")))
+_capi.set_option("grid", int(os.environ.get("PROF_GRID", "0")))
+_capi.set_option("config", int(os.environ.get("PROF_CONFIG", "10")))
+_capi.set_option("ppt", int(os.environ.get("PROF_PPT", "2")))
 hb = tile_batch(pack_batch([make_sample(i) for i in range(n_unique)]), reps)
 db = eng.upload(hb); out = eng.alloc_result(hb)
 for _ in range(launches):
