@@ -100,6 +100,7 @@ struct TableLayout {  // offsets (bytes) into the workspace
     size_t counter_off, boxprep_off, wedge_off, cullids_off;
     size_t boxscr_off, splitstats_off;  // merge scratch of samples processed in parts: per-box (count | min << 32, 3 biased sums) u64 x 4, per-sample stats + ticket
     size_t tileoff_off;                 // stream4.cu: [n_samples + 1] exclusive prefix of warp tiles per sample
+    size_t cls_off;                     // stream4.cu: per-CTA class words, [max CTAs][cull_dim^2 + kInnerMax^2] u32
     size_t total;
 };
 
@@ -110,10 +111,11 @@ int launch_stream_kernel(const FusedArgs& args, const TableLayout& T, unsigned c
 // stream4.cu (config 10)
 int stream4_misc_bytes();
 int stream4_queue_bytes(int ppt);
+int stream4_ring_bytes(int ppt);
 int stream4_threads(int ppt);
 int stream4_window_extra(int n_cull);
 void stream4_finish_layout(FusedLayout* L);
-int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, cudaStream_t stream, int* launches);
+int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream, int* launches);
 int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, cudaStream_t stream);
 
 // Per-edge classes of one cell against one wedge: bit0 = the wedge may contain points of the cell,

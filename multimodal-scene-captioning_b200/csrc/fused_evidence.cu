@@ -43,7 +43,7 @@ __device__ void compute_wedge(int image_w, const double* __restrict__ lcal, cons
 
 // grid: ceil(max(n_boxes_total, n_samples) * max(n_cams,1) / 256) blocks of 256 threads
 __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, int n_boxes_total,
-                                                          unsigned char* __restrict__ ws) {
+                                                          unsigned char* __restrict__ ws, uint32_t tile_pts) {
     const msc_params& P = A.P;
     const int n_cams = P.n_cams;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,6 +103,32 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
         compute_wedge(P.image_w, A.in.lidar_calib + (size_t)sample * 7, A.in.cam_calib + ((size_t)sample * n_cams + c) * 7,
                       A.in.cam_K + ((size_t)sample * n_cams + c) * 9, wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6);
     }
+    // (4) stream4.cu's static partition: tile_off[s] = warp tiles (tile_pts rows of one sweep) of samples [0, s); the last block scans
+    if (tile_pts != 0u && blockIdx.x == gridDim.x - 1) {
+        __shared__ uint32_t part[256];
+        uint32_t* const tile_off = reinterpret_cast<uint32_t*>(ws + T.tileoff_off);
+        const int n = A.in.n_samples, tid = threadIdx.x;
+        const int per = (n + 255) / 256;
+        const int s0 = min(tid * per, n), s1 = min(s0 + per, n);
+        auto tiles_of = [&](int s) {
+            uint32_t t = 0;
+            for (int w = A.in.sample_sweep_off[s]; w < A.in.sample_sweep_off[s + 1]; ++w) t += (A.in.sweep_count[w] + tile_pts - 1u) / tile_pts;
+            return t;
+        };
+        uint32_t sum = 0;
+        for (int s = s0; s < s1; ++s) sum += tiles_of(s);
+        part[tid] = sum;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {  // inclusive scan
+            const uint32_t v = tid >= d ? part[tid - d] : 0u;
+            __syncthreads();
+            part[tid] += v;
+            __syncthreads();
+        }
+        uint32_t run = part[tid] - sum;
+        for (int s = s0; s < s1; ++s) { tile_off[s] = run; run += tiles_of(s); }
+        if (tid == 255) tile_off[n] = part[255];
+    }
 }
 
 // Candidate-box ids per (sample, cull cell): conservative oriented rasterisation of every box footprint, one warp per box (lanes
@@ -135,8 +161,7 @@ struct msc_fused_ctx {
     int opt_window = 0;        // 0 = auto (largest that fits)
     int opt_cull_shift = -1;   // -1 = auto (cull cell ~ 2 m)
     int opt_fastdiv = 1;       // allow the Markstein division for whitelisted divisors
-    int opt_config = 0;        // 0 = auto (by how evenly whole samples fill the SMs); 10 / 7 force stream4.cu / fused_stream.cu
-                               // (fov_keep_mask != 0 always takes fused_stream.cu)
+    int opt_config = 0;        // 0 = auto: stream4.cu; 10 / 7 force stream4.cu / fused_stream.cu (fov_keep_mask != 0 always takes fused_stream.cu)
     int opt_grid = 0;          // stream4.cu: CTAs of the launch, 0 = auto (the SM count, fewer for batches of a few thousand rows)
     int opt_ppt = 2;           // stream4.cu: points per lane, 2 (768 threads) or 4 (512 threads)
     int opt_time_kernel = 0;   // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
@@ -183,6 +208,8 @@ static void cull_geometry(const msc_params& P, int opt_cull_shift, int* shift, i
     *dim = ((P.bev_res - 1) >> sh) + 1;
 }
 
+constexpr int kMaxGrid = 256;  // upper bound of the streaming kernels' grid (one CTA per SM)
+
 static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes, int cull_dim) {
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t ns = (size_t)(n_samples > 0 ? n_samples : 1), nb = (size_t)(n_boxes > 0 ? n_boxes : 1);
@@ -196,6 +223,7 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes,
     T.boxscr_off = off; off = align(off + nb * 32);
     T.splitstats_off = off; off = align(off + ns * MSC_STATS_STRIDE * 4);
     T.tileoff_off = off; off = align(off + (ns + 1) * 4);
+    T.cls_off = off; off = align(off + (size_t)kMaxGrid * (dim * dim + (size_t)kInnerMax * kInnerMax) * 4);
     T.total = off;
     return T;
 }
@@ -203,14 +231,14 @@ static TableLayout table_layout(const msc_params& P, int n_samples, int n_boxes,
 // shared-memory layout of either streaming kernel.  window_cell_bytes / window_extra: bytes per window cell and fixed bytes next to the
 // window (stream4.cu: two arrays + their sink and cull-cell words); inner_dim > 0 reserves a fine class table in smem.
 static int compute_layout(const msc_fused_ctx* X, const msc_params& P, int max_boxes_in_batch, int ring_bytes, int queue_bytes, int misc_bytes,
-                          int inner_dim, bool inner_in_smem, int window_extra, FusedLayout* L) {
+                          int inner_dim, bool inner_in_smem, int window_extra, int cull_cell_bytes, FusedLayout* L) {
     const int cap = max_boxes_in_batch < 1 ? 1 : max_boxes_in_batch;
     cull_geometry(P, X->opt_cull_shift, &L->cull_shift, &L->cull_dim);
     L->max_boxes = cap;
     int off = 0;
     L->tiles_off = off; off += ring_bytes; off = (off + 127) & ~127;
     L->queue_off = off; off += queue_bytes; off = (off + 127) & ~127;
-    L->cull_off = off; off += L->cull_dim * L->cull_dim * 8; off = (off + 127) & ~127;
+    L->cull_off = off; off += L->cull_dim * L->cull_dim * cull_cell_bytes; off = (off + 127) & ~127;
     L->boxp_off = off; off += cap * kBoxStride * 4;
     L->boxacc_off = off; off += cap * kAccWords * 4; off = (off + 127) & ~127;
     L->misc_off = off; off += (misc_bytes + 127) & ~127;
@@ -233,12 +261,14 @@ static int compute_layout(const msc_fused_ctx* X, const msc_params& P, int max_b
 
 // tables (prepared boxes, projection, wedges, housekeeping -> workspace), then the candidate-box ids of every cull cell; the per-cell
 // edge classes of the camera wedges are computed by the streaming kernels themselves, per sample, from the wedges
-static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, cudaStream_t stream) {
+static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int tile_pts,
+                         cudaStream_t stream) {
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
     if ((long long)args.in.n_samples * cams > work) work = (long long)args.in.n_samples * cams;
     X->last_launches = 0;
-    fused_tables_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(args, T, n_boxes_total, ws);
+    const unsigned blocks = (unsigned)((work + 255) / 256);
+    fused_tables_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(args, T, n_boxes_total, ws, (uint32_t)tile_pts);
     MSC_CUDA(cudaGetLastError());
     ++X->last_launches;
     if (n_boxes_total > 0 && args.L.max_boxes > 0) {
@@ -300,7 +330,7 @@ int msc_fused_set_option(msc_fused_ctx* X, const char* key, int32_t value) {
     if (!strcmp(key, "cull_shift")) { X->opt_cull_shift = value; return MSC_OK; }
     if (!strcmp(key, "fastdiv")) { X->opt_fastdiv = value ? 1 : 0; return MSC_OK; }
     if (!strcmp(key, "config")) { MSC_REQUIRE(value == 0 || value == 7 || value == 10, "config must be 0 (auto), 10 (stream4.cu) or 7 (fused_stream.cu)"); X->opt_config = value; return MSC_OK; }
-    if (!strcmp(key, "grid")) { MSC_REQUIRE(value >= 0 && value <= 4096, "grid out of range"); X->opt_grid = value; return MSC_OK; }
+    if (!strcmp(key, "grid")) { MSC_REQUIRE(value >= 0 && value <= kMaxGrid, "grid out of range"); X->opt_grid = value; return MSC_OK; }
     if (!strcmp(key, "ppt")) { MSC_REQUIRE(value == 2 || value == 4, "ppt must be 2 or 4"); X->opt_ppt = value; return MSC_OK; }
     if (!strcmp(key, "time_kernel")) { X->opt_time_kernel = value ? 1 : 0; return MSC_OK; }
     set_error("unknown option %s", key);
@@ -389,14 +419,7 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     // classes a FOV *filter* (fov_keep_mask) needs.
     const bool keepmask = fov && params->fov_keep_mask != 0u;
     int gen = keepmask ? 7 : X->opt_config;
-    if (gen == 0) {
-        // auto: fused_stream.cu hands out whole samples, so its last round of a batch leaves SMs idle; it is ~10 % faster per point (its
-        // TMA ring keeps the raw rows off the LSU data pipe, the unit both kernels saturate first) -- stream4.cu wins whenever the
-        // sample count is not close to a multiple of the SM count (a shard of a few dozen samples, a single keyframe, 404 samples ...)
-        const long long rounds = ((long long)in->n_samples + X->sms - 1) / X->sms;
-        const double fill = (double)in->n_samples / (double)(rounds * X->sms);
-        gen = fill >= 0.88 ? 7 : 10;
-    }
+    if (gen == 0) gen = 10;  // (on batches that fill the device the two kernels measure the same; stream4.cu also fills it on every other batch)
     X->last_fastdiv = fast ? 1 : 0;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     // fine edge classes for the kInnerMax x kInnerMax BEV cells around the sensor, where several image-column rays cross a 2 m cull cell
@@ -404,14 +427,14 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     inner &= ~1;
     int rc = -1;
     if (gen == 10) {
-        rc = compute_layout(X, *params, in->max_boxes_per_sample, 0, stream4_queue_bytes(X->opt_ppt), stream4_misc_bytes(), inner, true,
-                            stream4_window_extra(cdim * cdim), &args.L);
+        rc = compute_layout(X, *params, in->max_boxes_per_sample, stream4_ring_bytes(X->opt_ppt), stream4_queue_bytes(X->opt_ppt), stream4_misc_bytes(), inner, false,
+                            stream4_window_extra(cdim * cdim), 4, &args.L);
         if (rc == 0) stream4_finish_layout(&args.L);
         X->last_tile_pts = 32 * X->opt_ppt; X->last_threads = stream4_threads(X->opt_ppt);
     } else {
         int threads = 0, tile_pts = 0, ring = 0, queue = 0;
         stream_shape_info(&threads, &tile_pts, &ring, &queue);
-        rc = compute_layout(X, *params, in->max_boxes_per_sample, ring, queue, stream_misc_bytes(), inner, true, 0, &args.L);
+        rc = compute_layout(X, *params, in->max_boxes_per_sample, ring, queue, stream_misc_bytes(), inner, true, 0, 8, &args.L);
         X->last_tile_pts = tile_pts; X->last_threads = threads;
     }
     if (rc != 0) {
@@ -421,7 +444,7 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     X->last_config = gen;
     X->last_window = args.L.win_w;
     X->last_smem = args.L.total_bytes;
-    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, stream)) != MSC_OK) return rc;
+    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, gen == 10 ? 32 * X->opt_ppt : 0, stream)) != MSC_OK) return rc;
     int grid;
     if (gen == 10) {
         // every CTA gets the same number of warp tiles; a batch of a few thousand rows is not spread thinner than one tile per warp
@@ -430,7 +453,8 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
         const long long est_tiles = (long long)in->n_samples * ((pts + tile_pts - 1) / tile_pts);
         long long g = X->opt_grid > 0 ? X->opt_grid : est_tiles / warps;
         grid = (int)(g < 1 ? 1 : (g > X->sms ? X->sms : g));
-        if ((rc = launch_stream4_partition(args, T, ws, grid, X->opt_ppt, stream, &X->last_launches)) != MSC_OK) return rc;
+        if (grid > kMaxGrid) grid = kMaxGrid;
+        if ((rc = launch_stream4_partition(args, T, ws, grid, stream, &X->last_launches)) != MSC_OK) return rc;
     } else {
         grid = in->n_samples < X->sms ? in->n_samples : X->sms;
     }

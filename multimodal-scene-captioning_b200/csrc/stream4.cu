@@ -24,9 +24,11 @@ namespace msc {
 
 // Two launch shapes: PPT = 4 points per lane (512 threads x 128 registers, 128-row warp tiles read with 128-bit loads) and PPT = 2
 // (768 threads x 80 registers, 64-row warp tiles read with 64-bit loads: more warps to hide latency, less amortisation per tile).
-__host__ __device__ constexpr int s4_threads(int ppt) { return ppt == 4 ? 512 : 768; }
-constexpr int kS4MaxWarps = 24;
-constexpr int kS4QueueEntries = 128;  // per warp: drained 64 at a time, checked every two point slots (<= 63 pending + 64 pushed)
+__host__ __device__ constexpr int s4_threads(int ppt) { return ppt == 4 ? 512 : 1024; }
+constexpr int kS4MaxWarps = 32;
+// candidate queue per warp.  PPT = 4: 128 entries, drained 64 at a time (two per lane), checked every two point slots (<= 63 pending + 64
+// pushed); PPT = 2: 64 entries, drained 32 at a time, checked after every point slot (<= 31 pending + 32 pushed)
+__host__ __device__ constexpr int s4_queue_entries(int ppt) { return ppt == 4 ? 128 : 64; }
 constexpr int kS4PoseSmem = 12;   // sweeps whose transforms / extents are staged per sample; later ones are read from global memory
 constexpr int kS4SinkWords = 64;  // per array: [0, 32) remove_close sink of lane l, [32, 64) range / height sink of lane l
 constexpr uint32_t kS4CodeShift = 27, kS4CountMask = (1u << kS4CodeShift) - 1u, kS4CodeMulti = 31u;
@@ -38,6 +40,7 @@ struct alignas(16) S4Edge {  // one entry per edge code: the exact test of that 
 constexpr int kS4PairCodes = 14;  // codes 17..30: cells crossed by exactly two rays of different cameras, assigned per sample as they occur
 
 struct S4Misc {  // small per-CTA state at misc_off
+    uint64_t full_bar[kS4MaxWarps * 2];  // [warp][slot]: the bulk copy's bytes have landed in that warp's ring slot
     // [code]: 0 = pad (the test fails: a = NaN); 1 + c right edge, 9 + c left edge of camera c; 17 + i the first / second edge of pair i
     // (edge2 is a pad for every other code); 31 = several edges, resolved on a cold path from the cell's class word
     S4Edge edge1[32], edge2[32];
@@ -54,7 +57,8 @@ struct S4Misc {  // small per-CTA state at misc_off
 };
 
 int stream4_misc_bytes() { return (int)sizeof(S4Misc); }
-int stream4_queue_bytes(int ppt) { return (s4_threads(ppt) / 32) * kS4QueueEntries * 16; }
+int stream4_queue_bytes(int ppt) { return (s4_threads(ppt) / 32) * s4_queue_entries(ppt) * 16; }
+int stream4_ring_bytes(int ppt) { return (s4_threads(ppt) / 32) * 2 * (32 * ppt * 20); }  // per warp: two slots of one warp tile of raw rows
 int stream4_threads(int ppt) { return s4_threads(ppt); }
 int stream4_window_extra(int n_cull) { return 2 * ((kS4SinkWords + n_cull + 3) & ~3) * 4; }  // (+ 8 bytes per window cell)
 void stream4_finish_layout(FusedLayout* L) {
@@ -88,14 +92,6 @@ __device__ __forceinline__ uint32_t s4_lds32(uint32_t saddr) {
 __device__ __forceinline__ void s4_lds_f64x2(uint32_t saddr, double& a, double& b) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(saddr));
 }
-// streaming loads of raw rows: read once, evict first
-__device__ __forceinline__ void s4_ldg_stream128(const float* p, float* v) {
-    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void s4_ldg_stream64(const float* p, float* v) {
-    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
-}
-
 // predicated global reductions (one instruction each, no branch-around sequence)
 __device__ __forceinline__ void s4_red_global_u64_if(unsigned long long* p, unsigned long long v, bool pred) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.global.add.u64 [%0], %1;\n}" ::"l"(p), "l"(v), "r"((uint32_t)pred) : "memory");
@@ -128,34 +124,6 @@ __device__ __forceinline__ void s4_bev_cell_xy(float x, float y, float r, float 
 __device__ __forceinline__ uint32_t s4_decided_in(uint32_t cls) { return cls & ~(cls >> 8) & ~(cls >> 16) & 0xffu; }
 
 // ------------------------------------------------------------------------------------------------ partition pre-kernels
-// tile_off[s] = warp tiles (128 rows of one sweep) of samples [0, s); one block.
-__global__ void __launch_bounds__(1024) stream4_tileoff_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws,
-                                                               uint32_t tile_pts) {
-    __shared__ uint32_t part[1024];
-    uint32_t* const tile_off = reinterpret_cast<uint32_t*>(ws + T.tileoff_off);
-    const int n = A.in.n_samples, tid = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int s0 = min(tid * per, n), s1 = min(s0 + per, n);
-    auto tiles_of = [&](int s) {
-        uint32_t t = 0;
-        for (int w = A.in.sample_sweep_off[s]; w < A.in.sample_sweep_off[s + 1]; ++w) t += (A.in.sweep_count[w] + tile_pts - 1u) / tile_pts;
-        return t;
-    };
-    uint32_t sum = 0;
-    for (int s = s0; s < s1; ++s) sum += tiles_of(s);
-    part[tid] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan
-        const uint32_t v = tid >= d ? part[tid - d] : 0u;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    uint32_t run = part[tid] - sum;
-    for (int s = s0; s < s1; ++s) { tile_off[s] = run; run += tiles_of(s); }
-    if (tid == 1023) tile_off[n] = part[1023];
-}
-
 // Samples that straddle a CTA boundary of the static partition merge their parts with reductions: zero their output layers and merge
 // scratch first.  Block b looks at boundary b + 1 of a G-CTA launch; the first boundary inside a sample does the work.
 __global__ void __launch_bounds__(256) stream4_straddle_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws, int G) {
@@ -189,17 +157,20 @@ __global__ void __launch_bounds__(256) stream4_straddle_kernel(const __grid_cons
 template <bool FOV, bool FASTDIV, int PPT>
 __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
                                                                      unsigned char* __restrict__ ws) {
-    constexpr int NT = s4_threads(PPT), W = NT / 32, TP = 32 * PPT, TSH = PPT == 4 ? 7 : 6, RW = 5 * PPT;  // RW: words of a lane's rows
+    constexpr int NT = s4_threads(PPT), W = NT / 32, TP = 32 * PPT, TSH = PPT == 4 ? 7 : 6, kS4QueueEntries = s4_queue_entries(PPT);
     extern __shared__ __align__(128) unsigned char smem[];
     const msc_params& P = A.P;
     const FusedLayout& L = A.L;
     const int n_cull = L.cull_dim * L.cull_dim;
     uint32_t* const cullids = reinterpret_cast<uint32_t*>(smem + L.cull_off);   // [n_cull] candidate box ids of the cull cell
-    uint32_t* const cullcls = cullids + n_cull;                                 // [n_cull] its class word
+    // class words (camera in-bits and undecided-edge bits) of the cull cells and of the fine cells around the sensor: only the prologue
+    // (which turns them into edge codes), the epilogue and the cold multi-edge path read them, so they live in a per-CTA slice of the
+    // workspace (L1 / L2 hits) and leave 20 KB of shared memory to the BEV window
+    uint32_t* const cullcls = reinterpret_cast<uint32_t*>(ws + T.cls_off) + (size_t)blockIdx.x * (size_t)(n_cull + kInnerMax * kInnerMax);  // [n_cull]
+    uint32_t* const inner = cullcls + n_cull;                                   // [inner_dim^2] fine classes (one per BEV cell around the sensor)
     float* const boxp = reinterpret_cast<float*>(smem + L.boxp_off);            // [max_boxes][kBoxStride]
     uint32_t* const boxacc = reinterpret_cast<uint32_t*>(smem + L.boxacc_off);  // [max_boxes][kAccWords]
     S4Misc* const misc = reinterpret_cast<S4Misc*>(smem + L.misc_off);
-    uint32_t* const inner = reinterpret_cast<uint32_t*>(smem + L.inner_off);    // fine classes (one per BEV cell around the sensor)
     const int win_w = L.win_w, win_lo = L.win_lo;
     const int n_win = win_w * win_w;
     // window region: array A = [64 sink][n_win count | code << 27][n_cull periphery count | code << 27], array B = the same shape with
@@ -220,6 +191,10 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     asm volatile("" : "+r"(smem_s));  // opaque: one live register instead of a re-derived generic->shared conversion per use
     const uint32_t misc_s = smem_s + (uint32_t)L.misc_off;
     const uint32_t queue_s = smem_s + (uint32_t)L.queue_off + (uint32_t)warp * (uint32_t)(kS4QueueEntries * 16);  // this warp's candidate queue
+    constexpr uint32_t kSlotBytes = (uint32_t)TP * 20u;
+    const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * (2u * kSlotBytes);  // this warp's two slots of raw rows
+    const uint32_t bar_s = misc_s + (uint32_t)offsetof(S4Misc, full_bar) + (uint32_t)warp * 16u;  // and their two mbarriers
+    const uint64_t policy = l2_policy_evict_first();
     const uint32_t edge1_s = misc_s + (uint32_t)offsetof(S4Misc, edge1);
     constexpr uint32_t kEdge2 = (uint32_t)(offsetof(S4Misc, edge2) - offsetof(S4Misc, edge1)), kInc1 = (uint32_t)(offsetof(S4Misc, inc1) - offsetof(S4Misc, edge1)),
                        kInc2 = (uint32_t)(offsetof(S4Misc, inc2) - offsetof(S4Misc, edge1));
@@ -233,6 +208,14 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     const size_t ncell = (size_t)res * (size_t)res;
     const int n_cams = P.n_cams;
     const int n_inner = L.inner_dim * L.inner_dim;
+
+    if (lane == 0) {
+        mbar_init(&misc->full_bar[warp * 2 + 0], 1);
+        mbar_init(&misc->full_bar[warp * 2 + 1], 1);
+        mbar_fence_init();
+    }
+    uint32_t wk = 0;  // tiles this warp has consumed since launch: slot = wk & 1, mbarrier parity = (wk >> 1) & 1
+    __syncthreads();
 
     // ------------------------------------------------------------ this CTA's share of the batch: a range of global tiles
     const uint32_t* const tile_off = reinterpret_cast<const uint32_t*>(ws + T.tileoff_off);  // [n_samples + 1]
@@ -290,37 +273,25 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 s_te += (s_cnt + (uint32_t)(TP - 1)) >> TSH;
             }
         };
-        // Two register sets hold the lane's PPT rows: (x y z i) r | (x y z i) r | ...  One is consumed while the other is in flight;
-        // neither is ever copied (a copy would wait for the load right after issuing it).
-        float raw[2][RW];
-        int n_valid[2] = {0, 0};  // rows of the lane's group that exist (>= 4: all)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int k = 0; k < RW; ++k) raw[h][k] = 0.0f;
-        auto issue = [&](float (&r)[RW], int& nv) {  // whole warp (uniform control flow)
-            const uint32_t first = ((t - s_tb) << TSH) + (uint32_t)lane * (uint32_t)PPT;
-            nv = (int)s_cnt - (int)first;
+        // Raw rows travel global -> shared memory with the TMA unit (cp.async.bulk, completion on the warp's own mbarrier): the copy
+        // costs the LSU data pipe nothing -- five strided 64/128-bit loads per lane re-touch every 128-byte line five times there, and that
+        // pipe is what the kernel saturates first -- and no registers.  Two slots per warp: the successor of the tile being processed.
+        auto issue = [&](uint32_t slot) {  // whole warp (uniform control flow); one lane talks to the TMA unit
+            const uint32_t first = (t - s_tb) << TSH;
+            const uint32_t npts = min((uint32_t)TP, s_cnt - first);
+            const uint32_t bytes = (npts * 20u + 15u) & ~15u;
             const float* src = A.in.points + ((size_t)s_base + first) * 5;
-            if (((t - s_tb + 1u) << TSH) <= s_cnt) {  // a full tile
-                if constexpr (PPT == 4) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) s4_ldg_stream128(src + 4 * k, r + 4 * k);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) s4_ldg_stream64(src + 2 * k, r + 2 * k);
-                }
-            } else if constexpr (PPT == 4) {  // last tile of the sweep: only the 16-byte pieces that hold rows of this sweep (the buffer ends 16 bytes after its last row)
-                if (nv >= 1) { s4_ldg_stream128(src, r); s4_ldg_stream128(src + 4, r + 4); }
-                if (nv >= 2) s4_ldg_stream128(src + 8, r + 8);
-                if (nv >= 3) s4_ldg_stream128(src + 12, r + 12);
-                if (nv >= 4) s4_ldg_stream128(src + 16, r + 16);
-            } else {  // (8-byte pieces: a single row needs words 0..3 -> three pieces, 4 bytes past its end)
-                if (nv >= 1) { s4_ldg_stream64(src, r); s4_ldg_stream64(src + 2, r + 2); s4_ldg_stream64(src + 4, r + 4); }
-                if (nv >= 2) { s4_ldg_stream64(src + 6, r + 6); s4_ldg_stream64(src + 8, r + 8); }
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + slot * 8u), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                        ring_s + slot * kSlotBytes),
+                    "l"(src), "r"(bytes), "r"(bar_s + slot * 8u), "l"(policy)
+                    : "memory");
             }
         };
         bool more = t < lr1;
+        if (more) { seek_sweep(); issue(wk & 1u); }  // overlaps the prologue below
 
         // ------------------------------------------------------------ prologue: accumulators, tables -> smem
         const int bx0 = A.in.sample_box_off[sample];
@@ -409,8 +380,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
         // ------------------------------------------------------------ main loop: this warp's tiles, no cross-warp sync
         uint32_t c_ground = 0;             // per-thread counter (flushed once per sample)
         uint32_t cam_lo = 0, cam_hi = 0;   // eight 8-bit per-camera counters of the exact edge tests, spilled every <= 255 points
-        uint32_t pstate = 0;  // bits 0-7: points since the byte counters were spilled; bit 8: which register set holds the current tile;
-                              // bits 9-31: the fold of the ring values (see below)
+        uint32_t pstate = 0;  // points since the byte counters were spilled
         uint32_t q_head = 0, q_tail = 0;   // warp-uniform (every lane derives them from the same ballots)
         // Every lane tests TWO queued points (entries head + lane and head + 32 + lane) against their candidate boxes, one candidate of
         // each per trip, so two independent box tests are in flight per lane; the (usually single) containing box is accumulated once
@@ -469,9 +439,6 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             if (hit1 >= 0) accumulate(hit1, e1);
             q_head += n_take;
         };
-        // (the first tile's loads go out here, not before the prologue: values that live through the prologue are scattered over the
-        // register file and the loop would copy every reloaded set back into those places)
-        if (more) { seek_sweep(); issue(raw[0], n_valid[0]); }
         while (more) {
             // the transform of the tile that is consumed now (n_si is still its sweep: the cursor advances further down); recomputed per
             // tile rather than carried in registers
@@ -482,43 +449,49 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 __syncwarp();
                 pose_s = misc_s + (uint32_t)offsetof(S4Misc, wpose) + (uint32_t)warp * 96u;
             }
-            // ---- phase A: branch-free over the lane's points so their dependency chains interleave.  The part that reads the raw rows
-            // exists twice, once per register set (the rest of the loop body is shared: two full copies do not fit the instruction cache)
+            // ---- the tile in flight becomes the current one; its successor takes the slot consumed in the previous iteration
+            const uint32_t npts = min((uint32_t)TP, s_cnt - ((t - s_tb) << TSH));
+            t += (uint32_t)W;
+            more = t < lr1;
+            if (more) { seek_sweep(); issue((wk + 1u) & 1u); }
+            {
+                const uint32_t bar = bar_s + (wk & 1u) * 8u, parity = (wk >> 1) & 1u;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "MSC_S4WAIT_%=:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra MSC_S4DONE_%=;\n"
+                    "bra MSC_S4WAIT_%=;\n"
+                    "MSC_S4DONE_%=:\n"
+                    "}\n" ::"r"(bar),
+                    "r"(parity)
+                    : "memory");
+            }
+            // ---- phase A: branch-free over the lane's points so their dependency chains interleave.  Lane l owns rows l, l + 32, ... of
+            // the tile (a 5-word stride between lanes: bank-conflict free, and the 32 lanes of a slot hold 32 different rings)
             float xr[PPT], yr[PPT], zr[PPT];
             uint32_t q[PPT];
             bool close[PPT];
             {
                 double xd[PPT], yd[PPT], zd[PPT];
-                auto consume = [&](float (&rc)[RW], const int nv, float (&rn)[RW], int& nvn) {
-                    if (__any_sync(0xffffffffu, nv < PPT)) {  // last tile of a sweep: rows past its end -> NaN fails every compare below
-                        // (written into the loaded registers themselves: a separate copy of x would cost a move per point in every tile)
+                const uint32_t row_s = ring_s + (wk & 1u) * kSlotBytes + (uint32_t)lane * 20u;
+                ++wk;
 #pragma unroll
-                        for (int u = 0; u < PPT; ++u)
-                            if (u >= nv) rc[5 * u] = __int_as_float(0x7fc00000);
-                    }
-                    // (the four ring values are folded into a word nobody needs: all twenty registers of a set are then live across the
-                    // loop's back edge and become free together; a ring register that is never read is dead from the load on, gets
-                    // recycled for a long-lived value, and each 128-bit load into the set is followed by copies that wait for it --
-                    // a few LOP3 per tile buy the whole prefetch)
-#pragma unroll
-                    for (int u = 0; u < PPT; u += 2) pstate ^= (__float_as_uint(rc[5 * u + 4]) ^ __float_as_uint(rc[5 * u + 9])) & 0xfffffe00u;
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
-                        const float x = rc[5 * u], y = rc[5 * u + 1], z = rc[5 * u + 2], inten = rc[5 * u + 3];
-                        // A.1 remove_close (square, sweep's own sensor frame)
-                        close[u] = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
-                        // Q8 intensity, clamp [0, 65535], NaN -> 0: fmaxf drops NaN and negatives, the FFMA rounds v * 2^shift to nearest even
-                        // in the low mantissa bits of 2^23 + v * 2^shift (exact while below 2^23; larger values clamp anyway)
-                        q[u] = min(__float_as_uint(__fmaf_rn(fmaxf(inten, 0.0f), A.iscale, 8388608.0f)) - 0x4b000000u, 65535u);
-                        xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
-                    }
-                    // ---- the raw rows are consumed: the next tile's loads go out now and land while this one is processed
-                    t += (uint32_t)W;
-                    more = t < lr1;
-                    if (more) { seek_sweep(); issue(rn, nvn); }
-                };
-                if (pstate & 0x100u) consume(raw[1], n_valid[1], raw[0], n_valid[0]); else consume(raw[0], n_valid[0], raw[1], n_valid[1]);
-                pstate ^= 0x100u;
+                for (int u = 0; u < PPT; ++u) {
+                    float x = __uint_as_float(s4_lds32(row_s + u * 640u));
+                    const float y = __uint_as_float(s4_lds32(row_s + u * 640u + 4u)), z = __uint_as_float(s4_lds32(row_s + u * 640u + 8u));
+                    const float inten = __uint_as_float(s4_lds32(row_s + u * 640u + 12u));
+                    // last tile of a sweep: rows past its end hold stale data -> NaN fails every compare below
+                    if (npts < (uint32_t)TP && (uint32_t)lane + (uint32_t)u * 32u >= npts) x = __int_as_float(0x7fc00000);
+                    // A.1 remove_close (square, sweep's own sensor frame)
+                    close[u] = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
+                    // Q8 intensity, clamp [0, 65535], NaN -> 0: fmaxf drops NaN and negatives, the FFMA rounds v * 2^shift to nearest even
+                    // in the low mantissa bits of 2^23 + v * 2^shift (exact while below 2^23; larger values clamp anyway)
+                    q[u] = min(__float_as_uint(__fmaf_rn(fmaxf(inten, 0.0f), A.iscale, 8388608.0f)) - 0x4b000000u, 65535u);
+                    xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
+                }
+                __syncwarp();  // every lane has read its rows: the slot may be refilled at the top of the next iteration
                 // A.1 f64 matrix x f32 point -> f32, one matrix row at a time
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
@@ -638,21 +611,20 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                                  : "memory");
                 }
                 q_tail += __popc(m);
-                if (PPT == 4 && u == 1 && q_tail - q_head >= 64u) {  // (<= 63 + 64 pending here; two more slots add <= 64: the queue holds 128)
+                if (PPT == 4 ? (u == 1 && q_tail - q_head >= 64u) : (u == 0 && q_tail - q_head >= 32u)) {  // (so that the next slot(s) fit)
                     __syncwarp();
-                    drain_queue(64u);
+                    drain_queue(kDrain);
                 }
             }
             if (FOV) {
                 pstate += PPT;
-                if ((pstate & 0xffu) > 255u - PPT) {  // spill the byte counters before any of them can wrap
+                if (pstate > 255u - PPT) {  // spill the byte counters before any of them can wrap
 #pragma unroll
                     for (int c = 0; c < MSC_MAX_CAMS; ++c) {
                         const uint32_t v = ((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu;
                         if (v) atomicAdd(&misc->stats[5 + c], v);
                     }
-                    cam_lo = cam_hi = 0;
-                    pstate &= 0x100u;
+                    cam_lo = cam_hi = pstate = 0;
                 }
             }
         }
@@ -660,7 +632,6 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             __syncwarp();
             drain_queue(min(q_tail - q_head, kDrain));
         }
-        if ((pstate >> 9) == 0x1e3779u && A.cscale == -1.0f) misc->ticket = (int32_t)pstate;  // (never true: cscale is a positive power of two; keeps the fold alive)
 
         // ------------------------------------------------------------ epilogue
         __syncthreads();  // every tile of this part is accumulated
@@ -808,11 +779,8 @@ static int s4_launch_one(const FusedArgs& args, const TableLayout& T, unsigned c
     return MSC_OK;
 }
 
-// the two partition pre-kernels (tile prefix per sample; zero-fill of the samples that straddle CTA boundaries)
-int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, cudaStream_t stream, int* launches) {
-    stream4_tileoff_kernel<<<1, 1024, 0, stream>>>(args, T, ws, (uint32_t)(32 * ppt));
-    MSC_CUDA(cudaGetLastError());
-    ++*launches;
+// the partition pre-kernel (zero-fill of the samples that straddle CTA boundaries; the tile prefix per sample comes from fused_tables_kernel)
+int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream, int* launches) {
     if (grid > 1) {
         stream4_straddle_kernel<<<grid - 1, 256, 0, stream>>>(args, T, ws, grid);
         MSC_CUDA(cudaGetLastError());

@@ -213,7 +213,7 @@ def test_fused_static_partition_over_ctas(engine):
             for grid in (1, 2, 3, 7, 37, 148, 0):
                 _capi.set_option("grid", grid)
                 check_fused(engine, s, config=10)
-                assert _capi.get_option("last_config") == 10 and _capi.get_option("threads") == (512 if ppt == 4 else 768)
+                assert _capi.get_option("last_config") == 10 and _capi.get_option("threads") == (512 if ppt == 4 else 1024)
                 assert _capi.get_option("last_grid") == grid or grid == 0
         check_fused(engine, [make_sample(90, n_sweeps=1, n_boxes=60)], config=10)   # BASELINE config 2: one keyframe
         assert _capi.get_option("last_grid") > 1
