@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=0, help="stream4.cu: CTAs of the launch (0 = auto)")
     ap.add_argument("--ppt", type=int, default=0, help="stream4.cu: points per lane, 2 or 4 (0 = the library's default)")
     ap.add_argument("--cull-shift", type=int, default=-1)
+    ap.add_argument("--nccl-gather", action="store_true", help="gather the result tables with an NCCL all_gather instead of copy-engine peer pushes")
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")
     return ap.parse_args()
 
@@ -179,7 +180,7 @@ def main():
     import torch
     import torch.distributed as dist
     from msc_geom import _capi
-    from msc_geom.dist import TableGather, bind_to_gpu_numa
+    from msc_geom.dist import make_table_gather, bind_to_gpu_numa
     from msc_geom.engine import GeometryEngine
 
     numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation: staging buffers and copy threads stay on the GPU's socket
@@ -236,7 +237,8 @@ def main():
         _, arena_bytes = eng.table_layout(S, hb.n_boxes, params.n_cams)
         arena_bytes = int(max_over_ranks(float(arena_bytes)))  # ragged shards: every rank gathers the size of the largest
         outs = [eng.alloc_result(hb, arena_bytes=arena_bytes) for _ in range(2 if world > 1 else 1)]
-        gat = TableGather(arena_bytes, device=eng.device) if world > 1 else None  # NCCL only moves the small tables; BEV grids stay sharded
+        # only the small tables cross GPUs (BEV grids stay sharded): copy-engine pushes into peer memory, NCCL where that is unavailable
+        gat, gat_how = make_table_gather(arena_bytes, eng.device, prefer_peer=not args.nccl_gather) if world > 1 else (None, "none (1 GPU)")
 
         def step(k):
             out = outs[k % len(outs)]
@@ -259,6 +261,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
+        host_t0 = time.perf_counter()
         for k in range(steps):
             ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ka.record(stream)
@@ -270,6 +273,7 @@ def main():
                 eng.run_relations(rel_db, rel)
                 kc.record(stream)
                 rel_events.append((kb, kc))
+        host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / steps  # host time to queue one step (no synchronisation inside the loop)
         if gat is not None:
             gat.wait()
         e1.record(stream)
@@ -280,11 +284,18 @@ def main():
         call_ms = sum(a.elapsed_time(b) for a, b in call_events) / len(call_events)
         own = _capi.kernel_times(min(steps, 64))
         _capi.set_option("time_kernel", 0)
+        kernel_ms_here = (sum(own) / len(own)) if own else call_ms
+        per_rank_kernel_ms = [kernel_ms_here]
+        if world > 1:  # ranks stream different synthetic samples: the step ends with the slowest one
+            t = torch.tensor([kernel_ms_here], device="cuda", dtype=torch.float64)
+            allr = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            per_rank_kernel_ms = [round(float(x.item()), 4) for x in allr]
         total = strong if strong else world * S
         m = {"workload": wname_, "scaling": "strong" if strong else "weak", "total_samples": total, "samples_this_rank": S,
              "value": total * steps / (elapsed_ms * 1e-3), "unit": UNIT, "ms_per_step": elapsed_ms / steps, "steps": steps,
-             "call_ms": call_ms, "kernel_ms": (sum(own) / len(own)) if own else call_ms, "gpu_launches": eng.kernel_launches - launches0,
-             "kernel_config": _capi.get_option("last_config"),
+             "call_ms": call_ms, "kernel_ms": (sum(own) / len(own)) if own else call_ms, "host_enqueue_ms": host_enqueue_ms, "per_rank_kernel_ms": per_rank_kernel_ms, "gpu_launches": eng.kernel_launches - launches0,
+             "kernel_config": _capi.get_option("last_config"), "table_gather": gat_how + (" (one per step, double-buffered)" if world > 1 else ""),
              "grid": _capi.get_option("last_grid"), "bev_window_cells": _capi.get_option("last_window"),
              "tile_pts": _capi.get_option("tile_pts"), "threads": _capi.get_option("threads"), "table_arena_bytes": arena_bytes,
              "points_per_step_this_rank": hb.n_points, "algorithmic_bytes": algorithmic_bytes(hb, params), "n_unique": n_unique, "reps": reps}
@@ -385,10 +396,10 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kname = "stream3_kernel" if main["kernel_config"] == 9 else "stream_evidence_kernel"
+    kname = "stream4_kernel" if main["kernel_config"] == 10 else "stream_evidence_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "profiles/fused_traffic.json (one ncu --set full capture of the same launch shape, not this run)",
-                "kernel": kname, "kernel_ms": kavg_ms, "call_ms": main["call_ms"], "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
+                "kernel": kname, "kernel_ms": kavg_ms, "call_ms": main["call_ms"], "host_enqueue_ms": main["host_enqueue_ms"], "per_rank_kernel_ms": main["per_rank_kernel_ms"], "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src}
     cpu = None
     if not args.no_cpu and world == 1:
         n_cpu = args.cpu_samples or 16 * cores  # ~2 s wall on 16 threads = ~30 s of CPU work on the bounded sample
@@ -410,7 +421,7 @@ def main():
                        "l2_policy": "inputs (%.2f GB of raw rows per step) larger than L2; no explicit flush" % (main["points_per_step_this_rank"] * 20 / 1e9),
                        "fov_counts": bool(args.fov), "bev_window_cells": main["bev_window_cells"], "tile_pts": main["tile_pts"],
                        "threads": main["threads"], "kernel_config": main["kernel_config"], "grid": main["grid"],
-                       "table_gather": "one all_gather_into_tensor of the table arena per step on a side stream (double-buffered)" if world > 1 else "none (1 GPU)",
+                       "table_gather": main["table_gather"],
                        "table_arena_bytes": main["table_arena_bytes"]},
             "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "extra_workloads": extras}

@@ -90,6 +90,60 @@ class TableGather:
                     cur.wait_event(ev)
 
 
+class PeerTableGather:
+    """The same gather without a collective KERNEL: every rank PUSHES its arena into its row of every peer's gathered buffer with
+    copy-engine peer copies (symmetric memory over NVLink / NVSwitch; `Tensor.copy_` between peer-mapped buffers is a cudaMemcpyAsync
+    peer copy) on a side stream.  No SM is involved, so the copies of step k run under the streaming kernel of step k + 1 -- that
+    kernel holds every SM's shared memory, and an NCCL all-gather kernel queued beside it only starts in its tail (measured: 0.16 ms of
+    a 2.13 ms step at 8 GPUs).  `wait()` = own pushes done + a cross-rank barrier on the symmetric-memory signal pads: after it every
+    row of the most recent buffers is complete on every rank."""
+
+    def __init__(self, arena_bytes: int, device, depth: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.device, self.arena_bytes, self.depth = device, arena_bytes, depth
+        self.local = symm_mem.empty(depth * self.world * arena_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.local, dist.group.WORLD)
+        self.peer = [self.hdl.get_buffer(p, (depth, self.world, arena_bytes), torch.uint8) for p in range(self.world)]
+        self.side = torch.cuda.Stream(device=device)
+        self.done = [None] * depth
+        self.k = 0
+
+    def launch(self, arena: torch.Tensor) -> torch.Tensor:
+        slot = self.k % self.depth
+        self.k += 1
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)          # the tables of this step are complete
+        with torch.cuda.stream(self.side):
+            for j in range(self.world):      # staggered targets: at any moment every rank writes to a different peer
+                p = (self.rank + j) % self.world
+                self.peer[p][slot, self.rank].copy_(arena, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[slot] = ev
+        return self.peer[self.rank][slot]
+
+    def wait(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
+        self.hdl.barrier()                   # every peer's pushes into this rank's buffers are done as well
+
+
+def make_table_gather(arena_bytes: int, device, prefer_peer: bool = True):
+    """(gather object, description): the copy-engine gather where symmetric memory is available, else the NCCL / gloo collective."""
+    if prefer_peer and device is not None and torch.device(device).type == "cuda":
+        try:
+            return PeerTableGather(arena_bytes, device), "copy-engine pushes into peer (symmetric) memory, no collective kernel"
+        except Exception as e:  # noqa: BLE001 -- no symmetric memory on this platform / build
+            why = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:120] if str(e) else "")
+            return TableGather(arena_bytes, device=device), "one all_gather_into_tensor on a side stream (symmetric memory unavailable: %s)" % why
+    return TableGather(arena_bytes, device=device), "one all_gather_into_tensor on a side stream"
+
+
 def split_arena(buf: torch.Tensor, rank_layouts: Sequence[dict]) -> List[Dict[str, torch.Tensor]]:
     """Views of a gathered [world, arena_bytes] buffer as per-rank tables; rank_layouts[r] = GeometryEngine.table_layout(...)[0] plus
     a "shapes" entry {name: (dtype, shape)} for rank r's shard."""
