@@ -51,7 +51,9 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=0, help="stream4.cu: CTAs of the launch (0 = auto)")
     ap.add_argument("--ppt", type=int, default=0, help="stream4.cu: points per lane, 2 or 4 (0 = the library's default)")
     ap.add_argument("--cull-shift", type=int, default=-1)
-    ap.add_argument("--nccl-gather", action="store_true", help="gather the result tables with an NCCL all_gather instead of copy-engine peer pushes")
+    ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
+                    help="how the small result tables of the shards reach every GPU: fused = written into peer memory by the kernels that produce "
+                         "them (no gather step), peer = copy-engine pushes after the step, nccl = one all_gather_into_tensor after the step")
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples in the bounded CPU sample (0 = 4 x cores)")
     return ap.parse_args()
 
@@ -180,7 +182,7 @@ def main():
     import torch
     import torch.distributed as dist
     from msc_geom import _capi
-    from msc_geom.dist import make_table_gather, bind_to_gpu_numa
+    from msc_geom.dist import FusedTableGather, make_table_gather, bind_to_gpu_numa
     from msc_geom.engine import GeometryEngine
 
     numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation: staging buffers and copy threads stay on the GPU's socket
@@ -236,15 +238,29 @@ def main():
             rel, _ = eng.alloc_relations(rel_db.host)
         _, arena_bytes = eng.table_layout(S, hb.n_boxes, params.n_cams)
         arena_bytes = int(max_over_ranks(float(arena_bytes)))  # ragged shards: every rank gathers the size of the largest
-        outs = [eng.alloc_result(hb, arena_bytes=arena_bytes) for _ in range(2 if world > 1 else 1)]
-        # only the small tables cross GPUs (BEV grids stay sharded): copy-engine pushes into peer memory, NCCL where that is unavailable
-        gat, gat_how = make_table_gather(arena_bytes, eng.device, prefer_peer=not args.nccl_gather) if world > 1 else (None, "none (1 GPU)")
+        # only the small tables cross GPUs (BEV grids stay sharded).  Default: the kernels that produce a table entry store it into every
+        # GPU's gathered buffer themselves (P2P stores into peer-mapped memory); alternatives for comparison: copy-engine pushes, NCCL
+        gat, gat_how, reps_c = None, "none (1 GPU)", [None, None]
+        if world > 1 and args.gather == "fused":
+            try:
+                gat = FusedTableGather(arena_bytes, eng.device)
+                outs = [gat.result(eng, hb, k) for k in range(2)]
+                reps_c = [gat.replicas(eng, hb, k) for k in range(2)]
+                gat_how = "fused into the producing kernels: P2P stores into every GPU's gathered tables (symmetric memory), no gather step"
+            except Exception as e:  # noqa: BLE001 -- no symmetric memory on this platform / build
+                gat, gat_how = None, "symmetric memory unavailable (%s)" % type(e).__name__
+        if world > 1 and gat is None:
+            outs = [eng.alloc_result(hb, arena_bytes=arena_bytes) for _ in range(2)]
+            gat, how2 = make_table_gather(arena_bytes, eng.device, prefer_peer=args.gather != "nccl")
+            gat_how = how2 if gat_how.startswith("none") else how2 + "; " + gat_how
+        if world == 1:
+            outs = [eng.alloc_result(hb, arena_bytes=arena_bytes)]
 
         def step(k):
             out = outs[k % len(outs)]
             if gat is not None and gat.done[k % 2] is not None:
                 stream.wait_event(gat.done[k % 2])  # the gather that read this arena two steps ago is done
-            eng.run_fused(db, out)
+            eng.run_fused(db, out, replicas=reps_c[k % 2])
             if gat is not None:
                 gat.launch(out.table_arena)
 

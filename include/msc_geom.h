@@ -26,6 +26,7 @@ extern "C" {
 #define MSC_MAX_CAMS 8
 #define MSC_MAX_BOXES_FUSED 255 /* per sample, fused kernel (cull cells hold u8 box ids; 0xff = empty) */
 #define MSC_STATS_STRIDE 16
+#define MSC_MAX_REPLICAS 8 /* result-table replicas written by the fused kernels themselves (the other GPUs of one box) */
 
 typedef enum {
     MSC_OK = 0,
@@ -80,7 +81,7 @@ typedef struct {
 } msc_batch_in;
 
 /* Result tables.  bev_ci interleaves (count u32, intensity sum in Q<intensity_shift> u32) per cell so a
- * cell is one 8-byte word for the out-of-window 64-bit reductions; the kernel zero-fills it itself. */
+ * cell is one 8-byte word for the out-of-window 64-bit reductions; the kernels zero-fill it themselves. */
 typedef struct {
     uint32_t* box_count;   /* [n_boxes]           points inside the box (devkit points_in_box, App. A.2)  */
     float* box_nearest;    /* [n_boxes]           BEV distance of the nearest member point (+inf if none) */
@@ -107,12 +108,19 @@ int msc_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_ma
  * Replaces: LiDARAgent._preprocess_point_cloud / _segment_ground (lidar_agent.py:103-132) and the raster
  * half of _generate_multi_layer_bev (:539-560) for batches, plus the [EXT] rows e1-e5 of SURVEY.md
  * section 8(a) (devkit from_file_multisweep, points_in_box, get_sample_data/view_points/box_in_image).
- * Four launches: three small table kernels (prepared boxes + projection + camera wedges; per-cell edge classes, on the context's
- * side stream joined by an event; candidate-box ids per cull cell -> workspace) and the streaming kernel.  A batch with fewer samples
- * than the device has SMs is split over several CTAs per sample (integer accumulators: results do not depend on the split).
+ * Four launches: fused_tables_kernel (prepared boxes + box -> camera projection + camera wedges + the warp-tile prefix of the batch),
+ * fused_cullids_kernel (candidate-box ids per cull cell -> workspace), stream4_straddle_kernel (zero-fill of the samples that are
+ * processed in parts) and the streaming kernel stream4_kernel (csrc/stream4.cu).  The batch is partitioned statically in warp tiles:
+ * CTA b of G owns tiles [b T / G, (b + 1) T / G), so every SM streams the same number of points whatever the batch size; a sample that
+ * straddles CTA boundaries merges its parts with integer reductions (results do not depend on the partition).  fov_keep_mask != 0
+ * takes the one-sample-per-CTA kernel of csrc/fused_stream.cu (three launches).
  * workspace: >= msc_fused_workspace_bytes() bytes, 256-byte aligned, owned by the caller, one per stream in flight.
+ * Layout rules the library cannot check (the arrays are on the device; msc_geom.engine.DeviceBatch.check_layout does, on the host copy):
+ * sweep_start[] multiples of 4, the points buffer 16 bytes longer than the last sweep row.
+ * stats[13] bit 0 (a cell count reached 65536) covers the cells of the shared-memory window (the centre of the grid, where counts are
+ * high); cells outside it are accumulated with 64-bit global reductions and are not scanned.
  *
- * Context: options, the side stream, the timing ring and the facts about the last call live in an msc_fused_ctx, created on the current
+ * Context: options, the timing ring and the facts about the last call live in an msc_fused_ctx, created on the current
  * device.  Calls that share a context are serialised by it; contexts are independent, so host threads / streams / devices that each
  * own one never share mutable state.
  */
@@ -123,12 +131,23 @@ size_t msc_fused_workspace_bytes(const msc_fused_ctx* ctx, const msc_params* par
 int msc_fused_evidence_batch(msc_fused_ctx* ctx, const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same call for one shard of a batch that is spread over the GPUs of one box (samples are independent,
+ * only the small result tables are gathered).  replicas[r] describes where shard-local table entry i also has to land on peer r: the
+ * per-box tables, the projection tables and stats of replicas[r] must point at THIS shard's slice of peer r's gathered tables (device
+ * pointers into peer-mapped memory, e.g. torch symmetric memory; bev_* members are ignored -- BEV grids stay sharded).  The kernels that
+ * produce a table entry store it locally and through every replica (P2P stores over NVLink / NVSwitch), so there is no collective and no
+ * copy after the call; the caller only needs a cross-GPU barrier before the gathered tables are read.  n_replicas <= MSC_MAX_REPLICAS;
+ * n_replicas = 0 is msc_fused_evidence_batch.  Not available with fov_keep_mask != 0. */
+int msc_fused_evidence_batch_replicated(msc_fused_ctx* ctx, const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
+                                        int32_t n_replicas, const msc_batch_out* replicas_host, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
  * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv", "cull_shift" (-1 auto),
- * "config" (0 = auto, the default: stream3.cu when the batch is split over CTAs, fused_stream.cu otherwise; 9 / 7 force one;
- * fov_keep_mask != 0 always takes fused_stream.cu),
- * "split" (CTAs per sample, 0 = auto), "time_kernel".  get: also "last_window", "last_smem", "last_fastdiv", "last_split", "last_grid",
- * "last_config", "tile_pts", "threads", "last_launches". */
+ * "config" (0 = auto, the default: stream4.cu; 10 / 7 force stream4.cu / fused_stream.cu; fov_keep_mask != 0 always takes
+ * fused_stream.cu), "ppt" (stream4.cu launch shape: 2 = 1024 threads x 2 points per lane, 4 = 512 threads x 4), "grid" (CTAs of the
+ * stream4.cu launch, 0 = auto), "time_kernel".  get: also "last_window", "last_smem", "last_fastdiv", "last_grid", "last_config",
+ * "tile_pts", "threads", "last_launches". */
 int msc_fused_set_option(msc_fused_ctx* ctx, const char* key, int32_t value);
 int msc_fused_get_option(msc_fused_ctx* ctx, const char* key, int32_t* value);
 

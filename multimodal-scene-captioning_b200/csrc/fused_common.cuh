@@ -32,6 +32,11 @@ struct FusedArgs {
     float two_r, resf, rcp_two_r, cscale, iscale;
     int32_t centroid_bias;  // 2^(centroid_shift + 6): makes the quantised coordinate non-negative
     int32_t split;          // (unused since stream3.cu was retired: always 1)
+    // Replicas of the small result tables (per-box tables, projection tables, stats): the kernels that produce a value also store it
+    // through these pointers -- peer-mapped (symmetric) memory of the other GPUs of the box -- so the "gather" of a sharded batch is
+    // part of the producing kernels (P2P stores over NVLink / NVSwitch), not a collective after them.  bev_* members are ignored.
+    int32_t n_replicas;
+    msc_batch_out replica[MSC_MAX_REPLICAS];
 };
 
 // BEV cell index, lidar_agent.py:547-552.  FASTDIV replaces the IEEE division by the 3-instruction Markstein

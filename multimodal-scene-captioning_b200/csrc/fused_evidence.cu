@@ -96,6 +96,14 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
         project_box(A.in.boxes + (size_t)gb * 10, A.in.cam_ego_pose + ((size_t)sample * n_cams + c) * 7,
                     A.in.cam_calib + ((size_t)sample * n_cams + c) * 7, A.in.cam_K + ((size_t)sample * n_cams + c) * 9, (double)P.image_w,
                     (double)P.image_h, A.out.proj_visible + gid, A.out.proj_extent + (size_t)gid * 4);
+        if (A.n_replicas > 0) {  // the same entry on the other GPUs of the box (P2P stores)
+            const uint8_t vis = A.out.proj_visible[gid];
+            const float4 ext = *reinterpret_cast<const float4*>(A.out.proj_extent + (size_t)gid * 4);
+            for (int r = 0; r < A.n_replicas; ++r) {
+                A.replica[r].proj_visible[gid] = vis;
+                *reinterpret_cast<float4*>(A.replica[r].proj_extent + (size_t)gid * 4) = ext;
+            }
+        }
     }
     // (3) camera wedges: one thread per (sample, camera)
     if (n_cams > 0 && gid < A.in.n_samples * n_cams) {
@@ -377,8 +385,14 @@ int msc_fused_kernel_times(msc_fused_ctx* X, float* out_ms_host, int32_t n) {
 
 int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const msc_batch_in* in, const msc_batch_out* out, void* workspace,
                              size_t workspace_bytes, void* stream_v) {
+    return msc_fused_evidence_batch_replicated(X, params, in, out, 0, nullptr, workspace, workspace_bytes, stream_v);
+}
+
+int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* params, const msc_batch_in* in, const msc_batch_out* out,
+                                        int32_t n_replicas, const msc_batch_out* replicas, void* workspace, size_t workspace_bytes, void* stream_v) {
     using namespace msc;
     MSC_REQUIRE(X && params && in && out && workspace, "null argument");
+    MSC_REQUIRE(n_replicas >= 0 && n_replicas <= MSC_MAX_REPLICAS && (n_replicas == 0 || replicas), "n_replicas out of range");
     MSC_REQUIRE(in->n_samples >= 0 && in->n_boxes >= 0, "negative counts");
     MSC_REQUIRE(params->n_cams >= 0 && params->n_cams <= MSC_MAX_CAMS, "n_cams out of range");
     MSC_REQUIRE(params->bev_res > 0 && params->bev_res <= 4096 && (params->bev_res & 1) == 0, "bev_res must be even and <= 4096");
@@ -412,12 +426,16 @@ int msc_fused_evidence_batch(msc_fused_ctx* X, const msc_params* params, const m
     args.iscale = (float)(1 << params->intensity_shift);
     args.centroid_bias = 1 << (params->centroid_shift + 6);
     args.split = 1;
+    args.n_replicas = n_replicas;
+    for (int r = 0; r < n_replicas; ++r) args.replica[r] = replicas[r];
     const bool fov = X->opt_fov != 0 && params->n_cams > 0;
     const bool fast = X->opt_fastdiv != 0 && fastdiv_verified(args.two_r);
     // Kernel choice.  stream4.cu: rows read straight into registers, static partition of the batch in warp tiles (any batch size fills the
     // device evenly).  fused_stream.cu: the TMA-ring generation, one sample per CTA at a time -- the only one with the per-point wedge
     // classes a FOV *filter* (fov_keep_mask) needs.
     const bool keepmask = fov && params->fov_keep_mask != 0u;
+    MSC_REQUIRE(!(keepmask && n_replicas > 0), "replicated result tables are not available with fov_keep_mask != 0");
+    MSC_REQUIRE(!(X->opt_config == 7 && n_replicas > 0), "replicated result tables need the stream4.cu kernel (config 0 or 10)");
     int gen = keepmask ? 7 : X->opt_config;
     if (gen == 0) gen = 10;  // (on batches that fill the device the two kernels measure the same; stream4.cu also fills it on every other batch)
     X->last_fastdiv = fast ? 1 : 0;

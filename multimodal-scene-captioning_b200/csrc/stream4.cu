@@ -739,18 +739,23 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     for (int k = 0; k < 3; ++k) sum3[k] = __ldcg(scr + (size_t)b * 4 + 1 + k);
                 }
                 const size_t o = (size_t)(bx0 + b);
-                A.out.box_count[o] = cnt;
-                if (cnt == 0) {
-                    A.out.box_nearest[o] = INFINITY;
-                    A.out.box_centroid[o * 3 + 0] = 0.0f; A.out.box_centroid[o * 3 + 1] = 0.0f; A.out.box_centroid[o * 3 + 2] = 0.0f;
-                } else {
-                    A.out.box_nearest[o] = __fsqrt_rn(__uint_as_float(mn));
+                float nearest = INFINITY, cen[3] = {0.0f, 0.0f, 0.0f};
+                if (cnt != 0) {
+                    nearest = __fsqrt_rn(__uint_as_float(mn));
                     const double den = (double)cnt * (double)A.cscale;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const long long sum = (long long)sum3[k] - (long long)cnt * (long long)A.centroid_bias;
-                        A.out.box_centroid[o * 3 + k] = (float)((double)sum / den);
+                        cen[k] = (float)((double)sum / den);
                     }
+                }
+                A.out.box_count[o] = cnt;
+                A.out.box_nearest[o] = nearest;
+                A.out.box_centroid[o * 3 + 0] = cen[0]; A.out.box_centroid[o * 3 + 1] = cen[1]; A.out.box_centroid[o * 3 + 2] = cen[2];
+                for (int r = 0; r < A.n_replicas; ++r) {  // the same entry on the other GPUs of the box (P2P stores)
+                    A.replica[r].box_count[o] = cnt;
+                    A.replica[r].box_nearest[o] = nearest;
+                    A.replica[r].box_centroid[o * 3 + 0] = cen[0]; A.replica[r].box_centroid[o * 3 + 1] = cen[1]; A.replica[r].box_centroid[o * 3 + 2] = cen[2];
                 }
             }
             __syncthreads();  // (a straddling sample: misc->stats holds the merged counters)
@@ -765,6 +770,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 if (tid == 13 && box_overflow) v |= 0x80000000u;
                 if (tid == 15) v = 0u;
                 g_stats[tid] = v;
+                for (int r = 0; r < A.n_replicas; ++r) A.replica[r].stats[(size_t)sample * MSC_STATS_STRIDE + tid] = v;
             }
         }
     }

@@ -53,6 +53,8 @@ _PROTOS = {
     "msc_fused_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(MscParams), C.c_int32, C.c_int32]),
     "msc_fused_evidence_batch": (C.c_int, [C.c_void_p, C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
+    "msc_fused_evidence_batch_replicated": (C.c_int, [C.c_void_p, C.POINTER(MscParams), C.POINTER(MscBatchIn), C.POINTER(MscBatchOut), C.c_int32,
+                                                      C.POINTER(MscBatchOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "msc_fused_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "msc_fused_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)]),
     "msc_fused_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),

@@ -133,6 +133,40 @@ class PeerTableGather:
         self.hdl.barrier()                   # every peer's pushes into this rank's buffers are done as well
 
 
+class FusedTableGather:
+    """No gather step at all: the result tables of a shard are WRITTEN into every GPU's gathered buffer by the kernels that produce
+    them (msc_fused_evidence_batch_replicated: P2P stores through peer-mapped symmetric memory over NVLink / NVSwitch).  This object
+    only owns the buffers: `result(eng, hb, slot)` is a BatchResult whose table arena is this rank's row of its OWN gathered buffer,
+    `replicas(eng, hb, slot)` the C structs of the same row on every peer; `wait()` is the cross-GPU barrier after which every row of
+    every rank's buffers is complete."""
+
+    def __init__(self, arena_bytes: int, device, depth: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.device, self.arena_bytes, self.depth = device, arena_bytes, depth
+        self.local = symm_mem.empty(depth * self.world * arena_bytes, dtype=torch.uint8, device=device)
+        self.local.zero_()
+        self.hdl = symm_mem.rendezvous(self.local, dist.group.WORLD)
+        self.peer = [self.hdl.get_buffer(p, (depth, self.world, arena_bytes), torch.uint8) for p in range(self.world)]
+        self.done = [None] * depth           # (interface of the other gathers: nothing of this one is ever in flight on a side stream)
+
+    def result(self, eng, hb, slot: int, params=None):
+        return eng.alloc_result(hb, params, arena=self.peer[self.rank][slot, self.rank])
+
+    def replicas(self, eng, hb, slot: int, params=None):
+        return eng.replica_structs(hb, [self.peer[p][slot, self.rank] for p in range(self.world) if p != self.rank], params)
+
+    def gathered(self, slot: int) -> torch.Tensor:
+        return self.peer[self.rank][slot]
+
+    def launch(self, arena: torch.Tensor) -> None:  # the kernels already did it
+        return None
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+        self.hdl.barrier()
+
+
 def make_table_gather(arena_bytes: int, device, prefer_peer: bool = True):
     """(gather object, description): the copy-engine gather where symmetric memory is available, else the NCCL / gloo collective."""
     if prefer_peer and device is not None and torch.device(device).type == "cuda":

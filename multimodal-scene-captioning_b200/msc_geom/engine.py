@@ -40,6 +40,25 @@ class DeviceBatch:
     host: HostBatch
     tensors: Dict[str, torch.Tensor]
 
+    def check_layout(self) -> None:
+        """The layout rules of msc_batch_in that the library cannot check from the host (its arrays live on the device): every sweep
+        starts at a multiple of 4 rows (16-byte aligned bulk copies) and the points buffer extends at least 16 bytes past the last
+        row of every sweep.  A violation would be a misaligned or out-of-bounds cp.async.bulk inside the kernel; here it is an error
+        before the first launch (checked once per batch, on the host copy of the sweep table)."""
+        hb = self.host
+        if hb.sweep_start.size == 0:
+            return
+        start, count = hb.sweep_start.astype(np.int64), hb.sweep_count.astype(np.int64)
+        if (start % 4 != 0).any():
+            raise _capi.MscError("msc_batch_in: every sweep must start at a multiple of 4 rows (sweep %d starts at row %d)"
+                                 % (int(np.flatnonzero(start % 4)[0]), int(start[np.flatnonzero(start % 4)[0]])))
+        rows = int(self.tensors["points"].shape[0])
+        end = int((start + count).max())
+        if end * 20 + 16 > rows * 20:
+            raise _capi.MscError("msc_batch_in: the points buffer (%d rows) must extend 16 bytes past the last sweep row (%d)" % (rows, end))
+        if str(self.tensors["points"].dtype) != "torch.float32" or self.tensors["points"].shape[1] != 5 or not self.tensors["points"].is_contiguous():
+            raise _capi.MscError("msc_batch_in: points must be a contiguous (rows, 5) float32 tensor")
+
     def struct(self) -> MscBatchIn:
         """The C struct of this batch (built once: the tensors of a DeviceBatch never move)."""
         st = self.__dict__.get("_struct")
@@ -47,6 +66,7 @@ class DeviceBatch:
             t = self.tensors
             hb = self.host
             hint = int(hb.sweep_count.sum() // max(hb.n_samples, 1)) if hb.sweep_count.size else 0
+            self.check_layout()
             st = MscBatchIn(hb.n_samples, hb.max_boxes_per_sample, hb.n_boxes, min(hint, 2 ** 31 - 1), *[t[k].data_ptr() for k in _IN_FIELDS])
             self.__dict__["_struct"], self.__dict__["_struct_host"] = st, hb
         return st
@@ -223,14 +243,19 @@ class GeometryEngine:
             off = al(off + nbytes)
         return lay, max(off, 256)
 
-    def alloc_result(self, hb: HostBatch, params: Optional[GeomParams] = None, arena_bytes: Optional[int] = None) -> BatchResult:
+    def alloc_result(self, hb: HostBatch, params: Optional[GeomParams] = None, arena_bytes: Optional[int] = None,
+                     arena: Optional[torch.Tensor] = None) -> BatchResult:
         """Output buffers for `hb`.  The small tables live in ONE arena (`arena_bytes` pads it, e.g. to the largest shard of a job,
-        so every rank gathers the same size); the BEV layers, which stay sharded, are separate."""
+        so every rank gathers the same size; `arena` places it in caller-owned memory, e.g. this rank's row of a symmetric gathered
+        buffer); the BEV layers, which stay sharded, are separate."""
         p = params or self.params
         S, B, Cn, R = hb.n_samples, hb.n_boxes, p.n_cams, p.bev_res
         d = self.device
         lay, size = self.table_layout(S, B, Cn)
-        arena = torch.zeros(max(size, arena_bytes or 0), dtype=torch.uint8, device=d)
+        if arena is None:
+            arena = torch.zeros(max(size, arena_bytes or 0), dtype=torch.uint8, device=d)
+        elif arena.numel() < size or arena.dtype != torch.uint8:
+            raise _capi.MscError("alloc_result: the caller's arena is smaller than the tables (%d < %d bytes)" % (arena.numel(), size))
 
         def view(name, dtype, shape):
             o, n = lay[name]
@@ -243,7 +268,23 @@ class GeometryEngine:
             view("stats", torch.int32, (S, _capi.MSC_STATS_STRIDE)), arena)
 
     # ------------------------------------------------------------------ the hot path
-    def run_fused(self, db: DeviceBatch, out: Optional[BatchResult] = None, params: Optional[GeomParams] = None) -> BatchResult:
+    def replica_structs(self, hb: HostBatch, arenas: Sequence[torch.Tensor], params: Optional[GeomParams] = None):
+        """A C array of msc_batch_out for msc_fused_evidence_batch_replicated: entry r points at the six small tables laid out (like
+        alloc_result) in arenas[r] -- this shard's row of peer r's gathered buffer, peer-mapped memory.  BEV members stay null."""
+        p = params or self.params
+        lay, size = self.table_layout(hb.n_samples, hb.n_boxes, p.n_cams)
+        arr = (MscBatchOut * max(len(arenas), 1))()
+        for r, a in enumerate(arenas):
+            if a.numel() < size:
+                raise _capi.MscError("replica arena %d is smaller than the tables (%d < %d bytes)" % (r, a.numel(), size))
+            base = a.data_ptr()
+            arr[r] = MscBatchOut(base + lay["box_count"][0], base + lay["box_nearest"][0], base + lay["box_centroid"][0],
+                                 base + lay["proj_visible"][0], base + lay["proj_extent"][0], 0, 0, base + lay["stats"][0])
+        return arr, len(arenas)
+
+    def run_fused(self, db: DeviceBatch, out: Optional[BatchResult] = None, params: Optional[GeomParams] = None, replicas=None) -> BatchResult:
+        """One pass of the hot path over a device-resident batch.  `replicas` = replica_structs(...): the kernels also store every
+        small-table entry on those peers (the gather of a sharded batch without a collective)."""
         p = params or self.params
         if p.n_cams != db.host.n_cams:
             raise _capi.MscError(f"params.n_cams={p.n_cams} but the batch was packed for {db.host.n_cams} cameras")
@@ -262,8 +303,12 @@ class GeometryEngine:
         need = self._ws_need[wkey]
         if ws is None or ws.numel() < need:
             ws = self._workspaces[stream] = torch.zeros(need, dtype=torch.uint8, device=self.device)
-        _capi.check(self.lib.msc_fused_evidence_batch(self.ctx.handle, C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
-                                                      C.c_void_p(stream)), "msc_fused_evidence_batch")
+        if replicas is not None and replicas[1] > 0:
+            _capi.check(self.lib.msc_fused_evidence_batch_replicated(self.ctx.handle, C.byref(mp), C.byref(bi), C.byref(bo), replicas[1], replicas[0],
+                                                                     ws.data_ptr(), ws.numel(), C.c_void_p(stream)), "msc_fused_evidence_batch_replicated")
+        else:
+            _capi.check(self.lib.msc_fused_evidence_batch(self.ctx.handle, C.byref(mp), C.byref(bi), C.byref(bo), ws.data_ptr(), ws.numel(),
+                                                          C.c_void_p(stream)), "msc_fused_evidence_batch")
         self.kernel_launches += self.ctx.get_option("last_launches")  # table kernels + the streaming kernel, counted by the library
         return out
 

@@ -50,7 +50,7 @@ typedef struct {
     int32_t image_h;           /* 900  */
     int32_t n_cams;            /* 6    */
     uint32_t fov_keep_mask;    /* 0 = count only; else keep points inside any selected wedge      */
-    int32_t centroid_shift;    /* fixed-point fraction bits of centroid sums (20 for 50 m)       */
+    int32_t centroid_shift;    /* fixed-point fraction bits of centroid sums (<= 17: the biased coordinate is a 24-bit value)       */
     int32_t intensity_shift;   /* fixed-point fraction bits of intensity sums (8)                */
 } orc_params;
 

@@ -140,3 +140,23 @@ def test_token_only_scene_scan():
     assert len(toks) == 12 and toks[5] == "synth_sample_000005"
     assert ld.load_sample(toks[5])["sample_token"] == toks[5]
     assert len(create_loader(None, use_mock=True).scene_sample_tokens("mock_scene_001")) == 5
+
+
+def test_device_batch_layout_rules_are_checked_on_the_host():
+    """msc_batch_in's alignment / tail-padding rules (include/msc_geom.h) are enforced before the first launch."""
+    import pytest
+    import torch
+    from msc_geom import _capi
+    from msc_geom.engine import DeviceBatch
+    from msc_geom.layout import pack_batch
+    from msc_geom.synthetic import make_sample
+    import dataclasses
+    hb = pack_batch([make_sample(3, n_sweeps=2, n_boxes=2)])
+    pts = torch.from_numpy(hb.points)
+    DeviceBatch(hb, {"points": pts}).check_layout()
+    bad = dataclasses.replace(hb, sweep_start=hb.sweep_start + np.uint32(2))
+    with pytest.raises(_capi.MscError, match="multiple of 4"):
+        DeviceBatch(bad, {"points": pts}).check_layout()
+    end = int((hb.sweep_start.astype(np.int64) + hb.sweep_count).max())
+    with pytest.raises(_capi.MscError, match="16 bytes past"):
+        DeviceBatch(hb, {"points": pts[:end]}).check_layout()

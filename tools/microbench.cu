@@ -1,5 +1,5 @@
 // Microbenchmarks that fix the design constants of the fused evidence kernel on B200 (sm_100a).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o microbench microbench.cu
 // Each test prints one line; numbers are per-SM rates derived from CUDA-event time and SM clock.
 #include <cstdio>
 #include <cstdint>
