@@ -212,6 +212,36 @@ int msc_relation_table(int32_t n, const double* rect, float* dist, float* bearin
 int msc_relation_table_batch(int32_t n_samples, int32_t max_boxes, const int32_t* box_off, const int64_t* pair_off, const double* rect,
                              float* dist, float* bearing, uint8_t* category, uint8_t* overlap, void* stream);
 
+/*
+ * Camera-image decode for the on-disk step.  Replaces `np.array(Image.open(path))` in
+ * NuScenesLoader._load_camera (nuscenes_loader.py:136-144), i.e. libjpeg(-turbo)'s default decompression (ISLOW integer IDCT, "fancy"
+ * chroma upsampling, fixed-point YCbCr -> RGB), BIT-IDENTICALLY.  The entropy decode is sequential per image and runs on the host
+ * (msc_jpeg_entropy_decode_host: thread-safe, call it from one thread per image); dequantisation + IDCT + upsampling + colour
+ * conversion run on the device (msc_jpeg_reconstruct).  Baseline / extended-sequential Huffman, 8 bits, grayscale or JFIF YCbCr in
+ * one interleaved scan, 4:4:4 / 4:2:2 / 4:2:0, restart intervals; anything else returns MSC_ERR_UNSUPPORTED.
+ */
+typedef struct {
+    int32_t h, v;                /* sampling factors                                                  */
+    int32_t blocks_x, blocks_y;  /* 8x8 blocks per row / column of the (MCU-padded) component plane   */
+    int32_t ds_w, ds_h;          /* libjpeg's downsampled_width / downsampled_height                  */
+    int64_t coef_off;            /* first coefficient of the component in the coefficient buffer      */
+    int64_t plane_off;           /* first byte of the component in the plane scratch buffer           */
+    uint16_t qt[64];             /* quantisation table, natural (row-major) order                     */
+} msc_jpeg_comp;
+typedef struct {
+    int32_t width, height, n_comp, hmax, vmax, mcus_x, mcus_y, reserved_;
+    int64_t coef_elems;          /* int16 coefficients the entropy decode produces (all components)   */
+    int64_t plane_bytes;         /* device scratch for the component planes                           */
+    msc_jpeg_comp comp[3];
+} msc_jpeg_desc;
+/* host only: parse the headers of a JPEG stream held in host memory */
+int msc_jpeg_info(const uint8_t* jpeg_host, size_t nbytes, msc_jpeg_desc* desc_host);
+/* host only: Huffman-decode the scan into coef_host[desc->coef_elems] (per component: [blocks_y][blocks_x][64], natural order) */
+int msc_jpeg_entropy_decode_host(const uint8_t* jpeg_host, size_t nbytes, const msc_jpeg_desc* desc_host, int16_t* coef_host);
+/* device: coef (device, as produced above) -> out (device): [height, width, 3] RGB u8, or [height, width] for one component.
+ * planes: device scratch of desc->plane_bytes bytes. */
+int msc_jpeg_reconstruct(const msc_jpeg_desc* desc_host, const int16_t* coef, uint8_t* planes, uint8_t* out, void* stream);
+
 /* [EXT] standalone box -> camera projection (also fused into msc_fused_evidence_batch). */
 int msc_project_boxes(int32_t n_boxes, const double* boxes, int32_t n_cams, const double* cam_ego_pose,
                       const double* cam_calib, const double* cam_K, int32_t image_w, int32_t image_h,

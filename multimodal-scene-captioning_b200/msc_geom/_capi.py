@@ -42,6 +42,16 @@ class MscBatchOut(C.Structure):
     ]
 
 
+class MscJpegComp(C.Structure):
+    _fields_ = [("h", C.c_int32), ("v", C.c_int32), ("blocks_x", C.c_int32), ("blocks_y", C.c_int32), ("ds_w", C.c_int32), ("ds_h", C.c_int32),
+                ("coef_off", C.c_int64), ("plane_off", C.c_int64), ("qt", C.c_uint16 * 64)]
+
+
+class MscJpegDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_comp", C.c_int32), ("hmax", C.c_int32), ("vmax", C.c_int32), ("mcus_x", C.c_int32),
+                ("mcus_y", C.c_int32), ("reserved_", C.c_int32), ("coef_elems", C.c_int64), ("plane_bytes", C.c_int64), ("comp", MscJpegComp * 3)]
+
+
 _lib = None
 
 _PROTOS = {
@@ -76,6 +86,9 @@ _PROTOS = {
     "msc_dbscan_workspace_bytes": (C.c_size_t, [C.c_uint32, C.POINTER(C.c_int32)]),
     "msc_dbscan": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int32), C.c_void_p,
                              C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msc_jpeg_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(MscJpegDesc)]),
+    "msc_jpeg_entropy_decode_host": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(MscJpegDesc), C.c_void_p]),
+    "msc_jpeg_reconstruct": (C.c_int, [C.POINTER(MscJpegDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msc_cluster_views": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -83,13 +83,17 @@ class SyntheticNuScenesLoader:
 class NuScenesLoader:
     """Real-data loader: the reference's keys (nuscenes_loader.py:88-101) plus the additive multi-sweep keys."""
 
-    def __init__(self, dataroot: str, version: str = "v1.0-mini", n_sweeps: int = 10, lazy_sweeps: bool = False):
+    def __init__(self, dataroot: str, version: str = "v1.0-mini", n_sweeps: int = 10, lazy_sweeps: bool = False, engine=None):
         """lazy_sweeps: sweeps carry the .pcd.bin `path` instead of `points_raw` (and `point_cloud` / `images` are left out), so
-        msc_geom.io.stage_batch reads the files straight into one pinned batch buffer -- the on-disk step of the batched path."""
+        msc_geom.io.stage_batch reads the files straight into one pinned batch buffer -- the on-disk step of the batched path.
+        engine: a GeometryEngine; the six camera frames of a sample are then decoded by msc_geom.ops.decode_jpeg_batch (host Huffman
+        decode in parallel, IDCT / upsampling / colour conversion on the device) -- the same bytes as the reference's
+        np.array(Image.open(...)) (nuscenes_loader.py:136-144); files the decoder refuses (progressive, CMYK, PNG ...) go through PIL."""
         if not NUSCENES_AVAILABLE:
             raise ImportError("nuscenes-devkit is required. Install with: pip install nuscenes-devkit")
         from pathlib import Path
         self.dataroot, self.version, self.n_sweeps, self.lazy_sweeps = Path(dataroot), version, n_sweeps, lazy_sweeps
+        self.engine = engine
         self.nusc = NuScenes(version=version, dataroot=str(dataroot), verbose=True)
         self.camera_channels = list(CAMERA_CHANNELS)
 
@@ -100,19 +104,20 @@ class NuScenesLoader:
         return pose7(rec["translation"], rec["rotation"])
 
     def load_sample(self, sample_token: str) -> Dict:
-        from PIL import Image
         nusc = self.nusc
         sample = nusc.get("sample", sample_token)
-        images, names, cameras = [], [], []
+        images, names, cameras, image_paths = [], [], [], []
         for ch in self.camera_channels:
             if ch in sample["data"]:
                 sd = nusc.get("sample_data", sample["data"][ch])
                 if not self.lazy_sweeps:
-                    images.append(np.array(Image.open(self.dataroot / sd["filename"])))
+                    image_paths.append(self.dataroot / sd["filename"])
                 names.append(sd["channel"])
                 cs = nusc.get("calibrated_sensor", sd["calibrated_sensor_token"])
                 cameras.append({"channel": ch, "ego_pose": self._pose7(nusc.get("ego_pose", sd["ego_pose_token"])), "calib": self._pose7(cs),
                                 "intrinsic": np.asarray(cs["camera_intrinsic"], np.float64)})
+        if image_paths:
+            images = self._load_cameras(image_paths)
         ref_sd = nusc.get("sample_data", sample["data"]["LIDAR_TOP"])
         ref_pose = self._pose7(nusc.get("ego_pose", ref_sd["ego_pose_token"]))
         ref_cal = self._pose7(nusc.get("calibrated_sensor", ref_sd["calibrated_sensor_token"]))
@@ -141,6 +146,18 @@ class NuScenesLoader:
                 "annotations": annotations,
                 "metadata": {"location": nusc.get("log", scene["log_token"])["location"], "nbr_objects": len(annotations)},
                 "lidar_sweeps": sweeps, "ego_pose": ref_pose, "lidar_calib": ref_cal, "cameras": cameras}
+
+    def _load_cameras(self, paths) -> List[np.ndarray]:
+        """The sample's camera frames (reference: `_load_camera`, one np.array(Image.open(path)) per channel)."""
+        from PIL import Image
+        if self.engine is not None:
+            from . import ops
+            from ._capi import MscError
+            try:
+                return ops.decode_jpeg_batch(self.engine, [np.fromfile(str(p), dtype=np.uint8) for p in paths])
+            except MscError:
+                pass  # a flavour the device decoder refuses: the reference's decoder handles the whole sample
+        return [np.array(Image.open(p)) for p in paths]
 
     def scene_sample_tokens(self, scene_token: str) -> List[str]:
         """Tokens of a scene's samples from the table links alone (the reference's evaluator loads every image and point cloud

@@ -264,3 +264,44 @@ def dbscan(eng: GeometryEngine, xyz: np.ndarray, eps: float = 0.5, min_samples: 
                                    labels.data_ptr(), C.byref(k), ws.data_ptr(), need, _stream(eng)), "msc_dbscan")
     eng.kernel_launches += 8
     return labels.cpu().numpy().astype(np.int64)
+
+
+def decode_jpeg_batch(eng: GeometryEngine, streams, threads: int = 8, to_host: bool = True):
+    """Decode JPEG byte strings exactly like `np.array(PIL.Image.open(...))` (NuScenesLoader._load_camera, nuscenes_loader.py:136-144):
+    the Huffman decode of every image runs on a host thread (ctypes releases the GIL), coefficients go to the device in one copy per
+    image, dequantisation + IDCT + chroma upsampling + colour conversion run there.  Returns uint8 arrays (H, W, 3) -- (H, W) for
+    grayscale files -- on the host, or device tensors with to_host=False."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = eng.lib
+    bufs = [np.frombuffer(s, dtype=np.uint8) if not isinstance(s, np.ndarray) else s for s in streams]
+    descs, coefs = [], []
+    for b in bufs:
+        d = _capi.MscJpegDesc()
+        _capi.check(lib.msc_jpeg_info(b.ctypes.data, b.size, C.byref(d)), "msc_jpeg_info")
+        descs.append(d)
+        coefs.append(torch.empty(int(d.coef_elems), dtype=torch.int16).pin_memory())
+
+    def entropy(i):
+        return lib.msc_jpeg_entropy_decode_host(bufs[i].ctypes.data, bufs[i].size, C.byref(descs[i]), coefs[i].data_ptr())
+    if len(bufs) > 1 and threads > 1:
+        with ThreadPoolExecutor(max_workers=min(threads, len(bufs))) as pool:
+            rcs = list(pool.map(entropy, range(len(bufs))))
+    else:
+        rcs = [entropy(i) for i in range(len(bufs))]
+    for rc in rcs:
+        _capi.check(rc, "msc_jpeg_entropy_decode_host")
+    outs = []
+    for d, c in zip(descs, coefs):
+        cd = c.to(eng.device, non_blocking=True)
+        planes = torch.empty(int(d.plane_bytes), dtype=torch.uint8, device=eng.device)
+        shape = (d.height, d.width, 3) if d.n_comp == 3 else (d.height, d.width)
+        out = torch.empty(shape, dtype=torch.uint8, device=eng.device)
+        _capi.check(lib.msc_jpeg_reconstruct(C.byref(d), cd.data_ptr(), planes.data_ptr(), out.data_ptr(), _stream(eng)), "msc_jpeg_reconstruct")
+        outs.append(out)
+    if not to_host:
+        return outs
+    return [o.cpu().numpy() for o in outs]
+
+
+def decode_jpeg(eng: GeometryEngine, stream) -> np.ndarray:
+    return decode_jpeg_batch(eng, [stream], threads=1)[0]

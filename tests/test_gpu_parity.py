@@ -605,3 +605,91 @@ def test_bad_arguments_raise(engine):
         engine.run_fused(engine.upload(hb), params=GeomParams(bev_res=201))          # odd grid
     with pytest.raises(_capi.MscError):
         engine.run_fused(engine.upload(hb), params=GeomParams(n_cams=4))             # batch packed for 6 cameras
+
+
+# ------------------------------------------------------------------------------------------------ camera images (on-disk step)
+def _jpeg_bytes(img, **kw):
+    import io
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+@pytest.mark.gpu
+def test_jpeg_decode_equals_pil_bit_for_bit(engine):
+    """NuScenesLoader._load_camera is np.array(Image.open(path)) (nuscenes_loader.py:136-144): the device reconstruction (integer IDCT,
+    fancy chroma upsampling, fixed-point colour conversion) after the host Huffman decode must equal libjpeg-turbo's output exactly --
+    every subsampling PIL writes, odd sizes (partial MCUs, one-column chroma planes), optimised Huffman tables, restart intervals,
+    grayscale, and a nuScenes-sized frame."""
+    import io
+    from PIL import Image
+    from msc_geom import ops
+    rng = np.random.default_rng(11)
+
+    def scene(h, w):  # smooth structure + texture + hard edges, so that every coefficient band and the clamps are exercised
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        base = np.stack([127 + 120 * np.sin(xx / 17.0 + yy / 29.0), 127 + 120 * np.cos(xx / 7.0), 255 * ((xx // 13 + yy // 11) % 2)], -1)
+        return np.clip(base + rng.normal(0, 25, (h, w, 3)), 0, 255).astype(np.uint8)
+    cases = []
+    for (h, w) in ((16, 16), (17, 33), (1, 1), (2, 3), (3, 2), (8, 5), (9, 4), (31, 64), (240, 321)):
+        img = scene(h, w)
+        for sub in (0, 1, 2):
+            for q in (35, 90, 100):
+                cases.append(_jpeg_bytes(img, quality=q, subsampling=sub))
+        cases.append(_jpeg_bytes(img, quality=75, subsampling=2, optimize=True))
+        cases.append(_jpeg_bytes(img[..., 0].copy(), quality=80))  # grayscale
+    big = scene(900, 1600)
+    cases.append(_jpeg_bytes(big, quality=90, subsampling=2))
+    cases.append(_jpeg_bytes(rng.integers(0, 256, (64, 96, 3), dtype=np.uint8), quality=95, subsampling=2))  # noise: large coefficients, clamping
+    try:
+        cases.append(_jpeg_bytes(big[:200, :301], quality=85, subsampling=2, restart_marker_blocks=7))
+        cases.append(_jpeg_bytes(big[:100, :200], quality=85, subsampling=1, restart_marker_rows=1))
+    except TypeError:
+        pass
+    got = ops.decode_jpeg_batch(engine, cases, threads=4)
+    for i, (g, data) in enumerate(zip(got, cases)):
+        ref = np.array(Image.open(io.BytesIO(data)))
+        assert g.shape == ref.shape and g.dtype == np.uint8, (i, g.shape, ref.shape)
+        assert np.array_equal(g, ref), (i, ref.shape, int((g != ref).sum()), int(np.abs(g.astype(int) - ref.astype(int)).max()))
+    # unsupported flavours are refused, not mis-decoded
+    with pytest.raises(_capi.MscError):
+        ops.decode_jpeg(engine, _jpeg_bytes(big[:64, :64], progressive=True))
+    with pytest.raises(_capi.MscError):
+        ops.decode_jpeg(engine, b"not a jpeg at all")
+
+
+@pytest.mark.gpu
+def test_loader_camera_frames_through_the_device_decoder(engine, tmp_path):
+    """The loader mirror with an engine attached decodes the camera JPEGs of a written nuScenes tree on the device: same arrays as its
+    PIL path (the reference's np.array(Image.open(...)))."""
+    import importlib
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "devkit_shim")
+    sys.path.insert(0, shim)
+    try:
+        import msc_geom.nuscenes_loader as nl
+        nl = importlib.reload(nl)
+        from msc_geom import io as mio
+        rng = np.random.default_rng(3)
+        scenes = []
+        for si in range(1):
+            sc = []
+            for k in range(2):
+                s = make_sample(700 + 10 * si + k, n_sweeps=1, n_boxes=3)
+                s["images"] = [np.clip(rng.normal(128, 40, (90, 160, 3)), 0, 255).astype(np.uint8) for _ in s["cameras"]]
+                s["scene_name"], s["scene_description"] = f"scene-{si:04d}", "jpeg"
+                sc.append(s)
+            scenes.append(sc)
+        mio.write_nuscenes_tree(str(tmp_path), scenes)
+        a = nl.NuScenesLoader(str(tmp_path), "v1.0-mini", n_sweeps=1)
+        b = nl.NuScenesLoader(str(tmp_path), "v1.0-mini", n_sweeps=1, engine=engine)
+        for tok in a.scene_sample_tokens(a.get_scene_list()[0]["token"]):
+            ia, ib = a.load_sample(tok)["images"], b.load_sample(tok)["images"]
+            assert len(ia) == len(ib) == 6 and all(x.shape == (90, 160, 3) and np.array_equal(x, y) for x, y in zip(ia, ib))
+    finally:
+        sys.path.remove(shim)
+        for m in [m for m in sys.modules if m == "nuscenes" or m.startswith("nuscenes.")]:
+            del sys.modules[m]
+        import msc_geom.nuscenes_loader as nl2
+        importlib.reload(nl2)

@@ -160,3 +160,38 @@ def test_device_batch_layout_rules_are_checked_on_the_host():
     end = int((hb.sweep_start.astype(np.int64) + hb.sweep_count).max())
     with pytest.raises(_capi.MscError, match="16 bytes past"):
         DeviceBatch(hb, {"points": pts[:end]}).check_layout()
+
+
+def test_jpeg_header_parser_and_entropy_decoder_on_the_host():
+    """The host half of the camera-image decode (no GPU involved): headers of every flavour PIL writes, coefficient counts, DC terms of a
+    flat image, refusal of progressive files and garbage."""
+    import ctypes as C
+    import io
+    import pytest
+    from PIL import Image
+    from msc_geom import _capi
+    lib = _capi.load()
+
+    def enc(img, **kw):
+        b = io.BytesIO(); Image.fromarray(img).save(b, "JPEG", **kw); return np.frombuffer(b.getvalue(), dtype=np.uint8)
+    flat = np.full((20, 35, 3), 200, np.uint8)
+    for sub, (hmax, vmax) in ((0, (1, 1)), (1, (2, 1)), (2, (2, 2))):
+        data = enc(flat, quality=90, subsampling=sub)
+        d = _capi.MscJpegDesc()
+        assert lib.msc_jpeg_info(data.ctypes.data, data.size, C.byref(d)) == 0
+        assert (d.width, d.height, d.n_comp, d.hmax, d.vmax) == (35, 20, 3, hmax, vmax)
+        assert d.mcus_x == -(-35 // (8 * hmax)) and d.mcus_y == -(-20 // (8 * vmax))
+        assert d.coef_elems == sum(d.comp[c].blocks_x * d.comp[c].blocks_y * 64 for c in range(3))
+        coef = np.zeros(d.coef_elems, np.int16)
+        assert lib.msc_jpeg_entropy_decode_host(data.ctypes.data, data.size, C.byref(d), coef.ctypes.data) == 0
+        y = coef[:d.comp[0].blocks_x * d.comp[0].blocks_y * 64].reshape(-1, 64)
+        assert (y[:, 1:] == 0).all() and (y[0, 0] * d.comp[0].qt[0] > 0)      # a flat image has DC terms only (+ level shift)
+    prog = enc(flat, progressive=True)
+    d = _capi.MscJpegDesc()
+    assert lib.msc_jpeg_info(prog.ctypes.data, prog.size, C.byref(d)) == _capi_status("MSC_ERR_UNSUPPORTED")
+    junk = np.frombuffer(b"\x00\x01garbage", dtype=np.uint8)
+    assert lib.msc_jpeg_info(junk.ctypes.data, junk.size, C.byref(d)) < 0
+
+
+def _capi_status(name):
+    return {"MSC_ERR_BAD_ARGUMENT": -1, "MSC_ERR_LAUNCH": -2, "MSC_ERR_UNSUPPORTED": -3, "MSC_ERR_NO_DEVICE": -4}[name]

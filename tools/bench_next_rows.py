@@ -63,4 +63,22 @@ with tempfile.TemporaryDirectory() as d:
     mb = hb.points.nbytes / 1e6
     out["io_4x10_sweeps"] = {"megabytes": mb, "stage_in_place_pinned_ms": 1e3 * t_stage, "fromfile_then_pack_ms": 1e3 * t_ref,
                              "stage_GBps": mb / 1e3 / t_stage}
+# camera frames: six 1600x900 JPEGs (one sample) -- PIL (the reference's np.array(Image.open)) vs host Huffman + device reconstruction
+import io
+from PIL import Image
+rng = np.random.default_rng(5)
+yy, xx = np.mgrid[0:900, 0:1600].astype(np.float32)
+frames = []
+for c in range(6):
+    img = np.clip(np.stack([127 + 100 * np.sin(xx / (23.0 + c) + yy / 31.0), 127 + 100 * np.cos(xx / 11.0), 200 * ((xx // 40 + yy // 30) % 2)], -1)
+                  + rng.normal(0, 12, (900, 1600, 3)), 0, 255).astype(np.uint8)
+    b = io.BytesIO(); Image.fromarray(img).save(b, "JPEG", quality=90, subsampling=2); frames.append(b.getvalue())
+def pil_all():
+    return [np.array(Image.open(io.BytesIO(f))) for f in frames]
+pil_all(); t = time.perf_counter(); ref = pil_all(); t_pil = time.perf_counter() - t
+ops.decode_jpeg_batch(eng, frames, threads=6)
+t = time.perf_counter(); got = ops.decode_jpeg_batch(eng, frames, threads=6); t_dev = time.perf_counter() - t
+t = time.perf_counter(); got_d = ops.decode_jpeg_batch(eng, frames, threads=6, to_host=False); torch.cuda.synchronize(); t_dev_resident = time.perf_counter() - t
+out["jpeg_6x1600x900"] = {"pil_ms": 1e3 * t_pil, "device_ms_host_arrays_out": 1e3 * t_dev, "device_ms_device_tensors_out": 1e3 * t_dev_resident,
+                          "identical": bool(all(np.array_equal(a, b) for a, b in zip(ref, got))), "jpeg_kbytes": sum(len(f) for f in frames) / 1e3}
 print(json.dumps(out))
