@@ -21,6 +21,7 @@ struct FusedLayout {  // byte offsets into dynamic smem, computed on the host
     int32_t inner_off, inner_dim, inner_lo;  // fused_stream.cu: edge classes per BEV cell for cells [inner_lo, inner_lo + inner_dim)^2 (0: none)
     int32_t max_boxes;             // capacity of the smem box tables
     int32_t pcnt_off, isum_delta;  // stream4.cu: bytes from the window region's start to the cull-cell count words / from array A to array B
+    int32_t win_stride;            // stream4.cu: words between window rows (win_w + 1: odd, so rays along y do not pile up in one bank)
 };
 
 struct FusedArgs {
@@ -114,14 +115,13 @@ int stream_misc_bytes();
 void stream_shape_info(int* threads, int* tile_pts, int* ring_bytes, int* queue_bytes);
 int launch_stream_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream);
 // stream4.cu (config 10)
-int stream4_misc_bytes();
-int stream4_queue_bytes(int ppt);
-int stream4_ring_bytes(int ppt);
 int stream4_threads(int ppt);
-int stream4_window_extra(int n_cull);
-void stream4_finish_layout(FusedLayout* L);
+FusedLayout stream4_layout(int smem_bytes, int ppt, int res, int cull_dim, int cull_shift, int box_cap, int opt_window, int inner_dim);
+bool stream4_is_standard(const FusedArgs& a, int smem_bytes, int ppt, int opt_window);
+int stream4_std_boxes();
 int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream, int* launches);
-int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, cudaStream_t stream);
+int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, bool standard,
+                          cudaStream_t stream);
 
 // Per-edge classes of one cell against one wedge: bit0 = the wedge may contain points of the cell,
 // bit1 = the right edge is undecided inside the cell, bit2 = the left edge is.  Same extremes over the cell and the same guard band

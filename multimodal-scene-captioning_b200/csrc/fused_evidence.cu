@@ -171,7 +171,9 @@ struct msc_fused_ctx {
     int opt_fastdiv = 1;       // allow the Markstein division for whitelisted divisors
     int opt_config = 0;        // 0 = auto: stream4.cu; 10 / 7 force stream4.cu / fused_stream.cu (fov_keep_mask != 0 always takes fused_stream.cu)
     int opt_grid = 0;          // stream4.cu: CTAs of the launch, 0 = auto (the SM count, fewer for batches of a few thousand rows)
-    int opt_ppt = 2;           // stream4.cu: points per lane, 2 (768 threads) or 4 (512 threads)
+    int opt_ppt = 2;           // stream4.cu: points per lane, 2 (1024 threads) or 4 (512 threads)
+    int opt_std = 1;           // stream4.cu: allow the compile-time-constant instantiation for the standard configuration
+    int last_standard = 0;
     int opt_time_kernel = 0;   // bracket the streaming kernel with CUDA events (msc_fused_kernel_times)
     int last_window = 0, last_smem = 0, last_fastdiv = 0, last_tile_pts = 0, last_threads = 0, last_launches = 0, last_grid = 0, last_config = 0;
     bool ev_made = false;
@@ -340,6 +342,7 @@ int msc_fused_set_option(msc_fused_ctx* X, const char* key, int32_t value) {
     if (!strcmp(key, "config")) { MSC_REQUIRE(value == 0 || value == 7 || value == 10, "config must be 0 (auto), 10 (stream4.cu) or 7 (fused_stream.cu)"); X->opt_config = value; return MSC_OK; }
     if (!strcmp(key, "grid")) { MSC_REQUIRE(value >= 0 && value <= kMaxGrid, "grid out of range"); X->opt_grid = value; return MSC_OK; }
     if (!strcmp(key, "ppt")) { MSC_REQUIRE(value == 2 || value == 4, "ppt must be 2 or 4"); X->opt_ppt = value; return MSC_OK; }
+    if (!strcmp(key, "standard")) { X->opt_std = value ? 1 : 0; return MSC_OK; }
     if (!strcmp(key, "time_kernel")) { X->opt_time_kernel = value ? 1 : 0; return MSC_OK; }
     set_error("unknown option %s", key);
     return MSC_ERR_BAD_ARGUMENT;
@@ -356,6 +359,8 @@ int msc_fused_get_option(msc_fused_ctx* X, const char* key, int32_t* value) {
     if (!strcmp(key, "config")) { *value = X->opt_config; return MSC_OK; }
     if (!strcmp(key, "grid")) { *value = X->opt_grid; return MSC_OK; }
     if (!strcmp(key, "ppt")) { *value = X->opt_ppt; return MSC_OK; }
+    if (!strcmp(key, "standard")) { *value = X->opt_std; return MSC_OK; }
+    if (!strcmp(key, "last_standard")) { *value = X->last_standard; return MSC_OK; }
     if (!strcmp(key, "time_kernel")) { *value = X->opt_time_kernel; return MSC_OK; }
     if (!strcmp(key, "last_window")) { *value = X->last_window; return MSC_OK; }
     if (!strcmp(key, "last_smem")) { *value = X->last_smem; return MSC_OK; }
@@ -444,10 +449,14 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* para
     int inner = fov ? (params->bev_res < kInnerMax ? params->bev_res : kInnerMax) : 0;
     inner &= ~1;
     int rc = -1;
+    bool standard = false;
     if (gen == 10) {
-        rc = compute_layout(X, *params, in->max_boxes_per_sample, stream4_ring_bytes(X->opt_ppt), stream4_queue_bytes(X->opt_ppt), stream4_misc_bytes(), inner, false,
-                            stream4_window_extra(cdim * cdim), 4, &args.L);
-        if (rc == 0) stream4_finish_layout(&args.L);
+        // the box tables are sized for the standard capacity when the batch fits it, so that the layout -- and with it the choice of
+        // the compile-time-constant instantiation -- does not depend on the batch
+        const int cap = in->max_boxes_per_sample <= stream4_std_boxes() ? stream4_std_boxes() : in->max_boxes_per_sample;
+        args.L = stream4_layout(X->smem_optin, X->opt_ppt, params->bev_res, cdim, cshift, cap, X->opt_window, inner);
+        rc = args.L.win_w < 0 ? -1 : 0;
+        standard = rc == 0 && fast && stream4_is_standard(args, X->smem_optin, X->opt_ppt, X->opt_window) && X->opt_std != 0;
         X->last_tile_pts = 32 * X->opt_ppt; X->last_threads = stream4_threads(X->opt_ppt);
     } else {
         int threads = 0, tile_pts = 0, ring = 0, queue = 0;
@@ -478,7 +487,9 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* para
     }
     X->last_grid = grid;
     if ((rc = time_begin(X, stream)) != MSC_OK) return rc;
-    rc = gen == 10 ? launch_stream4_kernel(args, T, ws, grid, X->opt_ppt, fov, fast, stream) : launch_stream_kernel(args, T, ws, grid, fov, fast, stream);
+    rc = gen == 10 ? launch_stream4_kernel(args, T, ws, grid, X->opt_ppt, fov, fast, standard, stream)
+                   : launch_stream_kernel(args, T, ws, grid, fov, fast, stream);
+    X->last_standard = standard ? 1 : 0;
     if (rc != MSC_OK) return rc;
     ++X->last_launches;
     return time_end(X, stream);

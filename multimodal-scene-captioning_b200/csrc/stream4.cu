@@ -40,7 +40,6 @@ struct alignas(16) S4Edge {  // one entry per edge code: the exact test of that 
 constexpr int kS4PairCodes = 14;  // codes 17..30: cells crossed by exactly two rays of different cameras, assigned per sample as they occur
 
 struct S4Misc {  // small per-CTA state at misc_off
-    uint64_t full_bar[kS4MaxWarps * 2];  // [warp][slot]: the bulk copy's bytes have landed in that warp's ring slot
     // [code]: 0 = pad (the test fails: a = NaN); 1 + c right edge, 9 + c left edge of camera c; 17 + i the first / second edge of pair i
     // (edge2 is a pad for every other code); 31 = several edges, resolved on a cold path from the cell's class word
     S4Edge edge1[32], edge2[32];
@@ -56,16 +55,69 @@ struct S4Misc {  // small per-CTA state at misc_off
     float wq[MSC_MAX_CAMS * 6];     // this sample's camera wedges (fused_tables_kernel), source of the per-cell edge classes
 };
 
-int stream4_misc_bytes() { return (int)sizeof(S4Misc); }
-int stream4_queue_bytes(int ppt) { return (s4_threads(ppt) / 32) * s4_queue_entries(ppt) * 16; }
-int stream4_ring_bytes(int ppt) { return (s4_threads(ppt) / 32) * 2 * (32 * ppt * 20); }  // per warp: two slots of one warp tile of raw rows
 int stream4_threads(int ppt) { return s4_threads(ppt); }
-int stream4_window_extra(int n_cull) { return 2 * ((kS4SinkWords + n_cull + 3) & ~3) * 4; }  // (+ 8 bytes per window cell)
-void stream4_finish_layout(FusedLayout* L) {
-    const int n_win = L->win_w * L->win_w, n_cull = L->cull_dim * L->cull_dim;
-    L->pcnt_off = (kS4SinkWords + n_win) * 4;
-    L->isum_delta = (n_win + ((kS4SinkWords + n_cull + 3) & ~3)) * 4;
+
+// Shared-memory layout (bytes).  One block per warp first -- its two ring slots of raw rows, its candidate queue, its two mbarriers: one
+// base register reaches all of them with immediate offsets -- then the cull-cell ids, the small per-CTA state, the window region
+//   array A = [64 sink words][win_w^2 count | code << 27][cull_dim^2 periphery count | code << 27]
+//   array B = [64 sink words][win_w^2 Q8 intensity sums]
+// and, last, the box tables (their size is the only part that depends on the batch).  constexpr: the kernel instantiation for the
+// standard configuration takes every offset from here as a compile-time constant (immediate operands instead of constant-bank loads
+// and address arithmetic), the host uses the same function for every configuration.
+__host__ __device__ constexpr int s4_warp_block_bytes(int ppt) { return 2 * 32 * ppt * 20 + s4_queue_entries(ppt) * 16 + 16; }  // (a multiple of 16)
+__host__ __device__ constexpr FusedLayout s4_layout(int smem_bytes, int ppt, int res, int cull_dim, int cull_shift, int box_cap, int opt_window,
+                                                    int inner_dim) {
+    FusedLayout L{};
+    L.cull_dim = cull_dim; L.cull_shift = cull_shift; L.max_boxes = box_cap < 1 ? 1 : box_cap;
+    L.inner_dim = inner_dim; L.inner_lo = (res - inner_dim) / 2; L.inner_off = 0;
+    int off = 0;
+    L.tiles_off = off; L.queue_off = off; off += (s4_threads(ppt) / 32) * s4_warp_block_bytes(ppt);
+    L.cull_off = off; off += (cull_dim * cull_dim * 4 + 127) & ~127;
+    L.misc_off = off; off += ((int)sizeof(S4Misc) + 127) & ~127;
+    L.window_off = off;
+    const int n_cull_r = (kS4SinkWords + cull_dim * cull_dim + 3) & ~3;  // sink words + cull-cell words of array A, rounded
+    const int box_bytes = ((L.max_boxes * kBoxStride * 4 + L.max_boxes * kAccWords * 4) + 127) & ~127;
+    const int avail = smem_bytes - off - box_bytes - (n_cull_r + kS4SinkWords) * 4;
+    // window rows are stored with an ODD stride (win_w + 1 words): the 32 points of a warp slot lie along one ray from the sensor, and
+    // with a stride that is a multiple of 32 (96!) a ray along y would put all of them in one bank
+    int w = 0;
+    while ((w + 2) * (w + 3) * 8 <= avail && (w + 2) <= res) w += 2;
+    if (opt_window > 0 && opt_window < w) w = opt_window & ~1;
+    if (((res - w) / 2) & 1) w -= 2;  // keep win_lo even so flush rows stay 16-byte aligned in the global layer
+    if (w < 0) w = 0;
+    L.win_w = avail < 0 ? -1 : w;
+    L.win_lo = (res - w) / 2;
+    L.win_stride = w + 1;
+    const int n_store = w * (w + 1);
+    L.pcnt_off = (kS4SinkWords + n_store) * 4;
+    L.isum_delta = (n_store + n_cull_r) * 4;  // word of array A -> the same word of array B
+    off += (n_store + n_cull_r) * 4 + (kS4SinkWords + n_store) * 4;
+    L.boxp_off = off; off += L.max_boxes * kBoxStride * 4;
+    L.boxacc_off = off; off += L.max_boxes * kAccWords * 4;
+    L.total_bytes = (off + 127) & ~127;
+    return L;
 }
+// The standard configuration (BASELINE configs 2-5): 200 x 200 grid over +-50 m, 2 m cull cells, the reference's thresholds, up to
+// kS4StdBoxes boxes per sample, the B200's 227 KB of shared memory.
+constexpr int kS4StdSmem = 232448, kS4StdRes = 200, kS4StdCullDim = 50, kS4StdCullShift = 2, kS4StdBoxes = 128, kS4StdInner = kInnerMax;
+struct S4StdParams {  // msc_params / FusedArgs members the main loop reads, as the standard configuration has them (bit patterns of
+    // msc_geom.layout.GeomParams() / geometry.sqrt_thresholds)
+    static constexpr float remove_close_radius = 1.0f, s_lo = 0x1.000004p+0f, s_hi = 0x1.387ffep+11f, z_min = -3.0f, z_max = 5.0f,
+                           ground_z = -0x1.666666p+0f, bev_range = 50.0f, two_r = 100.0f, rcp_two_r = 0x1.47ae14p-7f, resf = 200.0f, iscale = 256.0f;
+};
+bool stream4_is_standard(const FusedArgs& a, int smem_bytes, int ppt, int opt_window) {
+    const msc_params& P = a.P;
+    typedef S4StdParams S;
+    if (ppt != 2 || smem_bytes != kS4StdSmem || opt_window != 0) return false;
+    if (P.bev_res != kS4StdRes || a.L.cull_dim != kS4StdCullDim || a.L.cull_shift != kS4StdCullShift || a.L.max_boxes > kS4StdBoxes) return false;
+    return P.remove_close_radius == S::remove_close_radius && P.s_lo == S::s_lo && P.s_hi == S::s_hi && P.z_min == S::z_min && P.z_max == S::z_max &&
+           P.ground_z == S::ground_z && P.bev_range == S::bev_range && a.two_r == S::two_r && a.rcp_two_r == S::rcp_two_r && a.resf == S::resf &&
+           a.iscale == S::iscale;
+}
+FusedLayout stream4_layout(int smem_bytes, int ppt, int res, int cull_dim, int cull_shift, int box_cap, int opt_window, int inner_dim) {
+    return s4_layout(smem_bytes, ppt, res, cull_dim, cull_shift, box_cap, opt_window, inner_dim);
+}
+int stream4_std_boxes() { return kS4StdBoxes; }
 
 // ---- shared-state-space accesses through 32-bit addresses (no generic-address arithmetic in the loop)
 __device__ __forceinline__ void s4_red_add(uint32_t saddr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
@@ -154,13 +206,21 @@ __global__ void __launch_bounds__(256) stream4_straddle_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ the streaming kernel
-template <bool FOV, bool FASTDIV, int PPT>
+template <bool FOV, bool FASTDIV, int PPT, bool STD>
 __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
                                                                      unsigned char* __restrict__ ws) {
     constexpr int NT = s4_threads(PPT), W = NT / 32, TP = 32 * PPT, TSH = PPT == 4 ? 7 : 6, kS4QueueEntries = s4_queue_entries(PPT);
     extern __shared__ __align__(128) unsigned char smem[];
-    const msc_params& P = A.P;
-    const FusedLayout& L = A.L;
+    // STD: every layout offset and every threshold of the main loop is a compile-time constant (the host selects this instantiation only
+    // when the call's layout and parameters equal them bit for bit, stream4_is_standard); otherwise they are kernel arguments
+    constexpr FusedLayout SL = s4_layout(kS4StdSmem, PPT, kS4StdRes, kS4StdCullDim, kS4StdCullShift, kS4StdBoxes, 0, kS4StdInner);
+    struct PV { float remove_close_radius, s_lo, s_hi, z_min, z_max, ground_z, bev_range; int bev_res, n_cams; };
+    const FusedLayout L = STD ? SL : A.L;
+    const PV P = STD ? PV{S4StdParams::remove_close_radius, S4StdParams::s_lo, S4StdParams::s_hi, S4StdParams::z_min, S4StdParams::z_max,
+                          S4StdParams::ground_z, S4StdParams::bev_range, kS4StdRes, A.P.n_cams}
+                     : PV{A.P.remove_close_radius, A.P.s_lo, A.P.s_hi, A.P.z_min, A.P.z_max, A.P.ground_z, A.P.bev_range, A.P.bev_res, A.P.n_cams};
+    const float two_r = STD ? S4StdParams::two_r : A.two_r, rcp_two_r = STD ? S4StdParams::rcp_two_r : A.rcp_two_r, resf = STD ? S4StdParams::resf : A.resf,
+                iscale = STD ? S4StdParams::iscale : A.iscale;
     const int n_cull = L.cull_dim * L.cull_dim;
     uint32_t* const cullids = reinterpret_cast<uint32_t*>(smem + L.cull_off);   // [n_cull] candidate box ids of the cull cell
     // class words (camera in-bits and undecided-edge bits) of the cull cells and of the fine cells around the sensor: only the prologue
@@ -171,13 +231,12 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     float* const boxp = reinterpret_cast<float*>(smem + L.boxp_off);            // [max_boxes][kBoxStride]
     uint32_t* const boxacc = reinterpret_cast<uint32_t*>(smem + L.boxacc_off);  // [max_boxes][kAccWords]
     S4Misc* const misc = reinterpret_cast<S4Misc*>(smem + L.misc_off);
-    const int win_w = L.win_w, win_lo = L.win_lo;
-    const int n_win = win_w * win_w;
-    // window region: array A = [64 sink][n_win count | code << 27][n_cull periphery count | code << 27], array B = the same shape with
-    // the Q8 intensity sums (its cull-cell part only absorbs the periphery points' adds)
+    const int win_w = L.win_w, win_lo = L.win_lo, win_stride = L.win_stride;
+    const int n_win = win_w * win_stride;  // words of a window array (rows padded to the odd stride)
+    // window region: array A = [64 sink][n_win count | code << 27][n_cull periphery count | code << 27], array B = [64 sink][n_win Q8
+    // intensity sums] (a periphery point adds its intensity to the lane's sink word of array B)
     uint32_t* const arrA = reinterpret_cast<uint32_t*>(smem + L.window_off);
-    const uint32_t arr_words = (uint32_t)(n_win + ((kS4SinkWords + n_cull + 3) & ~3));  // (n_win is a multiple of 4: both arrays stay 16-byte aligned)
-    uint32_t* const arrB = arrA + arr_words;
+    uint32_t* const arrB = arrA + (L.isum_delta >> 2);
     uint32_t* const wcount = arrA + kS4SinkWords;
     uint32_t* const pcnt = wcount + n_win;
     uint32_t* const wisum = arrB + kS4SinkWords;
@@ -190,10 +249,10 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     uint32_t smem_s = smem_u32(smem);
     asm volatile("" : "+r"(smem_s));  // opaque: one live register instead of a re-derived generic->shared conversion per use
     const uint32_t misc_s = smem_s + (uint32_t)L.misc_off;
-    const uint32_t queue_s = smem_s + (uint32_t)L.queue_off + (uint32_t)warp * (uint32_t)(kS4QueueEntries * 16);  // this warp's candidate queue
-    constexpr uint32_t kSlotBytes = (uint32_t)TP * 20u;
-    const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * (2u * kSlotBytes);  // this warp's two slots of raw rows
-    const uint32_t bar_s = misc_s + (uint32_t)offsetof(S4Misc, full_bar) + (uint32_t)warp * 16u;  // and their two mbarriers
+    constexpr uint32_t kSlotBytes = (uint32_t)TP * 20u, kWarpBlock = (uint32_t)s4_warp_block_bytes(PPT);
+    const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * kWarpBlock;  // this warp's block: two slots of raw rows,
+    const uint32_t queue_s = ring_s + 2u * kSlotBytes;                                     // its candidate queue
+    const uint32_t bar_s = queue_s + (uint32_t)(kS4QueueEntries * 16);                     // and its two mbarriers
     const uint64_t policy = l2_policy_evict_first();
     const uint32_t edge1_s = misc_s + (uint32_t)offsetof(S4Misc, edge1);
     constexpr uint32_t kEdge2 = (uint32_t)(offsetof(S4Misc, edge2) - offsetof(S4Misc, edge1)), kInc1 = (uint32_t)(offsetof(S4Misc, inc1) - offsetof(S4Misc, edge1)),
@@ -210,8 +269,8 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     const int n_inner = L.inner_dim * L.inner_dim;
 
     if (lane == 0) {
-        mbar_init(&misc->full_bar[warp * 2 + 0], 1);
-        mbar_init(&misc->full_bar[warp * 2 + 1], 1);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8u), "r"(1) : "memory");
         mbar_fence_init();
     }
     uint32_t wk = 0;  // tiles this warp has consumed since launch: slot = wk & 1, mbarrier parity = (wk >> 1) & 1
@@ -351,8 +410,8 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
         __threadfence();
         __syncthreads();  // class tables are in smem
         for (int i = tid; i < n_win; i += NT) {
-            const int wy = i / win_w, wx = i - wy * win_w;
-            wcount[i] = code_of(class_of(wx + win_lo, wy + win_lo)) << kS4CodeShift;
+            const int wy = i / win_stride, wx = i - wy * win_stride;
+            wcount[i] = wx < win_w ? code_of(class_of(wx + win_lo, wy + win_lo)) << kS4CodeShift : 0u;
         }
         __syncthreads();  // every pair that occurs has its code
         if (tid < 64) {
@@ -476,6 +535,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             {
                 double xd[PPT], yd[PPT], zd[PPT];
                 const uint32_t row_s = ring_s + (wk & 1u) * kSlotBytes + (uint32_t)lane * 20u;
+                const bool partial = npts < (uint32_t)TP;  // (warp-uniform)
                 ++wk;
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) {
@@ -483,12 +543,12 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     const float y = __uint_as_float(s4_lds32(row_s + u * 640u + 4u)), z = __uint_as_float(s4_lds32(row_s + u * 640u + 8u));
                     const float inten = __uint_as_float(s4_lds32(row_s + u * 640u + 12u));
                     // last tile of a sweep: rows past its end hold stale data -> NaN fails every compare below
-                    if (npts < (uint32_t)TP && (uint32_t)lane + (uint32_t)u * 32u >= npts) x = __int_as_float(0x7fc00000);
+                    if (partial && (uint32_t)lane + (uint32_t)u * 32u >= npts) x = __int_as_float(0x7fc00000);
                     // A.1 remove_close (square, sweep's own sensor frame)
                     close[u] = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
                     // Q8 intensity, clamp [0, 65535], NaN -> 0: fmaxf drops NaN and negatives, the FFMA rounds v * 2^shift to nearest even
                     // in the low mantissa bits of 2^23 + v * 2^shift (exact while below 2^23; larger values clamp anyway)
-                    q[u] = min(__float_as_uint(__fmaf_rn(fmaxf(inten, 0.0f), A.iscale, 8388608.0f)) - 0x4b000000u, 65535u);
+                    q[u] = min(__float_as_uint(__fmaf_rn(fmaxf(inten, 0.0f), iscale, 8388608.0f)) - 0x4b000000u, 65535u);
                     xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
                 }
                 __syncwarp();  // every lane has read its rows: the slot may be refilled at the top of the next iteration
@@ -513,8 +573,13 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             // ---- phase B: filter, BEV cell, cull entry, count word
             uint32_t cand[PPT], code[PPT];
             bool rare = false;
-            unsigned long long* const ci64g = *reinterpret_cast<unsigned long long* volatile*>(&misc->ci64);
-            int* const h32g = *reinterpret_cast<int* volatile*>(&misc->h32);
+            unsigned long long* ci64g;
+            int* h32g;
+            {
+                const uint2 a = s4_lds64(misc_s + (uint32_t)offsetof(S4Misc, ci64)), b = s4_lds64(misc_s + (uint32_t)offsetof(S4Misc, h32));
+                ci64g = reinterpret_cast<unsigned long long*>(((unsigned long long)a.y << 32) | a.x);
+                h32g = reinterpret_cast<int*>(((unsigned long long)b.y << 32) | b.x);
+            }
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
                 // lidar_agent.py:106-110, sqrt-free (thresholds on s are exact, geometry.sqrt_thresholds)
@@ -522,17 +587,17 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 const bool keep = !close[u] && (s2 >= P.s_lo) && (s2 <= P.s_hi) && (zr[u] < P.z_max) && (zr[u] > P.z_min);
                 // BEV cell, lidar_agent.py:547-552 (garbage for dropped points is clamped and never used)
                 uint32_t ix, iy;
-                s4_bev_cell_xy<FASTDIV>(xr[u], yr[u], P.bev_range, A.two_r, A.rcp_two_r, A.resf, (uint32_t)res_m1, ix, iy);
+                s4_bev_cell_xy<FASTDIV>(xr[u], yr[u], P.bev_range, two_r, rcp_two_r, resf, (uint32_t)res_m1, ix, iy);
                 const uint32_t ci = (iy >> L.cull_shift) * (uint32_t)L.cull_dim + (ix >> L.cull_shift);
                 const uint32_t ids = s4_lds32(cull_s + (ci << 2));
                 const uint32_t wx = ix - (uint32_t)win_lo, wy = iy - (uint32_t)win_lo;
                 const bool inwin = max(wx, wy) < (uint32_t)win_w;
                 // ---- phase C: the atomic that counts the point returns its cell's edge code.  Window cells count into the window, cells
                 // outside it into their cull cell's word, dropped points into one of the lane's two sink words (code 0)
-                uint32_t wa = inwin ? wcount_s + ((wy * (uint32_t)win_w + wx) << 2) : pcnt_s + (ci << 2);
+                uint32_t wa = inwin ? wcount_s + ((wy * (uint32_t)win_stride + wx) << 2) : pcnt_s + (ci << 2);
                 wa = keep ? wa : (close[u] ? sink_close_s : sink_gate_s);
                 const uint32_t old = s4_atom_add(wa, 1u);
-                s4_red_add(wa + isum_delta, q[u]);
+                s4_red_add((keep && !inwin) ? sink_close_s + isum_delta : wa + isum_delta, q[u]);
                 if (keep && zr[u] < P.ground_z) ++c_ground;  // lidar_agent.py:128
                 code[u] = old >> kS4CodeShift;
                 cand[u] = keep ? ids : kCullEmpty;
@@ -575,7 +640,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                             if (us == (uint32_t)u) { px = xr[u]; py = yr[u]; }
                         // the class the point's code came from: its cull cell's outside the window, else its BEV cell's
                         uint32_t cix, ciy;
-                        s4_bev_cell_xy<FASTDIV>(px, py, P.bev_range, A.two_r, A.rcp_two_r, A.resf, (uint32_t)res_m1, cix, ciy);
+                        s4_bev_cell_xy<FASTDIV>(px, py, P.bev_range, two_r, rcp_two_r, resf, (uint32_t)res_m1, cix, ciy);
                         const bool pp = max(cix - (uint32_t)win_lo, ciy - (uint32_t)win_lo) >= (uint32_t)win_w;
                         const uint32_t cls = pp ? cullcls[(ciy >> L.cull_shift) * L.cull_dim + (cix >> L.cull_shift)] : class_of((int)cix, (int)ciy);
                         uint32_t und = (cls >> 8) & 0xffffu, pass = 0xffffu;
@@ -657,8 +722,8 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             const int half_w = win_w >> 1;  // win_w and win_lo are even -> 16-byte aligned rows of the global layer
             for (int i = tid; i < win_w * half_w; i += NT) {
                 const int wy = i / half_w, wx = (i - wy * half_w) * 2;
-                const uint2 c2 = *reinterpret_cast<const uint2*>(wcount + wy * win_w + wx);
-                const uint2 s2 = *reinterpret_cast<const uint2*>(wisum + wy * win_w + wx);
+                const uint2 c2 = make_uint2(wcount[wy * win_stride + wx], wcount[wy * win_stride + wx + 1]);
+                const uint2 s2 = make_uint2(wisum[wy * win_stride + wx], wisum[wy * win_stride + wx + 1]);
                 const uint32_t c0 = c2.x & kS4CountMask, c1 = c2.y & kS4CountMask;
                 const int cx = wx + win_lo, cy = wy + win_lo;
                 const size_t cell = (size_t)cy * (size_t)res + (size_t)cx;
@@ -776,9 +841,9 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     }
 }
 
-template <bool FOV, bool FASTDIV, int PPT>
+template <bool FOV, bool FASTDIV, int PPT, bool STD>
 static int s4_launch_one(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, cudaStream_t stream) {
-    auto kern = stream4_kernel<FOV, FASTDIV, PPT>;
+    auto kern = stream4_kernel<FOV, FASTDIV, PPT, STD>;
     MSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, args.L.total_bytes));
     kern<<<grid, s4_threads(PPT), args.L.total_bytes, stream>>>(args, T, ws);
     MSC_CUDA(cudaGetLastError());
@@ -797,11 +862,15 @@ int launch_stream4_partition(const FusedArgs& args, const TableLayout& T, unsign
 
 template <int PPT>
 static int s4_launch_ppt(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, bool fov, bool fast, cudaStream_t stream) {
-    if (fov) return fast ? s4_launch_one<true, true, PPT>(args, T, ws, grid, stream) : s4_launch_one<true, false, PPT>(args, T, ws, grid, stream);
-    return fast ? s4_launch_one<false, true, PPT>(args, T, ws, grid, stream) : s4_launch_one<false, false, PPT>(args, T, ws, grid, stream);
+    if (fov) return fast ? s4_launch_one<true, true, PPT, false>(args, T, ws, grid, stream) : s4_launch_one<true, false, PPT, false>(args, T, ws, grid, stream);
+    return fast ? s4_launch_one<false, true, PPT, false>(args, T, ws, grid, stream) : s4_launch_one<false, false, PPT, false>(args, T, ws, grid, stream);
 }
 
-int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, cudaStream_t stream) {
+// standard: the compile-time-constant instantiation (stream4_is_standard() held for this call: PPT 2, the Markstein division applies)
+int launch_stream4_kernel(const FusedArgs& args, const TableLayout& T, unsigned char* ws, int grid, int ppt, bool fov, bool fast, bool standard,
+                          cudaStream_t stream) {
+    if (standard && ppt == 2 && fast)
+        return fov ? s4_launch_one<true, true, 2, true>(args, T, ws, grid, stream) : s4_launch_one<false, true, 2, true>(args, T, ws, grid, stream);
     return ppt == 4 ? s4_launch_ppt<4>(args, T, ws, grid, fov, fast, stream) : s4_launch_ppt<2>(args, T, ws, grid, fov, fast, stream);
 }
 

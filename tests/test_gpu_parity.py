@@ -52,6 +52,20 @@ def check_fused(eng, samples, params=None, config=None, n_cams=6):
 @pytest.mark.parametrize("config", [10, 7])
 def test_fused_config3_shape(engine, config):
     check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
+    if config == 10:  # the standard configuration takes the compile-time-constant instantiation of stream4.cu; the generic one must agree
+        assert _capi.get_option("last_standard") == 1
+        try:
+            _capi.set_option("standard", 0)
+            check_fused(engine, [make_sample(i, n_sweeps=10, n_boxes=60) for i in range(2)], config=config)
+            assert _capi.get_option("last_standard") == 0
+            check_fused(engine, [make_sample(5, n_sweeps=3, n_boxes=130)], config=config)       # more boxes than the standard capacity
+            _capi.set_option("standard", 1)
+            check_fused(engine, [make_sample(5, n_sweeps=3, n_boxes=130)], config=config)
+            assert _capi.get_option("last_standard") == 0
+            check_fused(engine, [make_sample(6, n_sweeps=3, n_boxes=128)], config=config)       # exactly the standard capacity
+            assert _capi.get_option("last_standard") == 1
+        finally:
+            _capi.set_option("standard", 1)
 
 
 def test_fused_mini_boxes_and_mixed_sweeps(engine):
@@ -91,22 +105,24 @@ def test_fused_crowded_cell_and_max_boxes(engine):
 
 
 def test_fused_under_declared_max_boxes_sets_the_flag(engine):
-    """A caller that under-declares max_boxes_per_sample: the first max_boxes boxes are exact, the overflow bit of stats[13] is set,
-    everything that does not depend on boxes is unaffected -- in both kernel generations."""
+    """A caller that under-declares max_boxes_per_sample: the boxes the kernel has room for are exact (fused_stream.cu: the declared
+    number; stream4.cu sizes its tables for at least 128 boxes), the overflow bit of stats[13] is set for a sample with more,
+    everything that does not depend on boxes is unaffected -- in both kernels."""
     import dataclasses
     import torch
-    s = [make_sample(45, n_sweeps=2, n_boxes=12), make_sample(46, n_sweeps=1, n_boxes=4)]
+    s = [make_sample(45, n_sweeps=2, n_boxes=140), make_sample(46, n_sweeps=1, n_boxes=4)]
     hb = pack_batch(s)
     p = GeomParams()
     cut = dataclasses.replace(hb, max_boxes_per_sample=5)
     for cfg in DEFAULT_CONFIGS:
+        room = 128 if cfg == 10 else 5
         _capi.set_option("config", cfg)
         out = engine.run_fused(engine.upload(cut), params=p); torch.cuda.synchronize()
         got = out.to_host()
         for i in range(2):
             ref = OB.oracle_fused(hb, i, p)
             b0 = hb.sample_box_off[i]
-            n_ok = min(5, hb.sample_box_off[i + 1] - b0)
+            n_ok = min(room, hb.sample_box_off[i + 1] - b0)
             for k in ("box_count", "box_nearest", "box_centroid"):
                 assert np.array_equal(got[k][b0:b0 + n_ok], ref[k][:n_ok]), (cfg, i, k)
             for k in ("proj_visible", "proj_extent"):

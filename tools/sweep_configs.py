@@ -22,8 +22,10 @@ ref = None
 rows = []
 for cs in configs:
     cfg, split = cs[0], (cs[1] if len(cs) > 1 else 0)
-    if cfg >= 100:  # 102 / 104: stream4.cu with 2 / 4 points per lane
-        _capi.set_option("ppt", cfg % 100)
+    _capi.set_option("standard", 1)
+    if cfg >= 100:  # 102 / 104: stream4.cu with 2 / 4 points per lane; 112: 2 points per lane without the compile-time-constant instantiation
+        _capi.set_option("ppt", cfg % 10)
+        _capi.set_option("standard", 0 if (cfg // 10) % 10 == 1 else 1)
         cfg = 10
     _capi.set_option("config", cfg)
     _capi.set_option("grid", split)  # (second field of a spec: CTAs of the stream4.cu launch, 0 = auto)
@@ -57,7 +59,7 @@ for cs in configs:
     torch.cuda.synchronize()
     kt = _capi.kernel_times(iters)
     _capi.set_option("time_kernel", 0)
-    row = {"config": cfg, "ppt": _capi.get_option("ppt"), "grid": _capi.get_option("last_grid"), "ms": round(ms, 4), "kernel_ms": round(sum(kt) / len(kt), 4), "samples_per_s": round(hb.n_samples / ms * 1e3), "vs_first": same,
+    row = {"config": cfg, "ppt": _capi.get_option("ppt"), "standard": _capi.get_option("last_standard"), "grid": _capi.get_option("last_grid"), "ms": round(ms, 4), "kernel_ms": round(sum(kt) / len(kt), 4), "samples_per_s": round(hb.n_samples / ms * 1e3), "vs_first": same,
            "window": _capi.get_option("last_window"), "threads": _capi.get_option("threads"), "tile_pts": _capi.get_option("tile_pts")}
     rows.append(row)
     print(json.dumps(row), flush=True)
