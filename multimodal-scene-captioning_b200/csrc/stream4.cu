@@ -44,8 +44,6 @@ struct S4Misc {  // small per-CTA state at misc_off
     // (edge2 is a pad for every other code); 31 = several edges, resolved on a cold path from the cell's class word
     S4Edge edge1[32], edge2[32];
     uint2 inc1[32], inc2[32];  // byte-counter increments (cameras 0-3, 4-7) of the entry's camera
-    unsigned long long* ci64;  // this sample's (count, isum) layer as 64-bit cells and its max-height layer, read back by the
-    int* h32;                  // global reductions (the 80-register shape would otherwise re-derive the two pointers per point)
     uint32_t pairs[16];  // pair i: 0 = free, else 0x100 | e1 | e2 << 4 (edge numbers 0-7 right, 8-15 left)
     uint32_t stats[MSC_STATS_STRIDE];
     uint32_t sweep_start[kS4PoseSmem], sweep_count[kS4PoseSmem];
@@ -312,10 +310,6 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
         for (int i = tid; i < min(n_sw, kS4PoseSmem) * 12; i += NT) misc->pose[i] = A.in.sweep_pose[(size_t)sw0 * 12 + i];
         if (tid < MSC_STATS_STRIDE) { misc->stats[tid] = 0u; misc->pairs[tid] = 0u; }
         if (FOV && tid < MSC_MAX_CAMS * 6) misc->wq[tid] = g_wedges[(size_t)sample * MSC_MAX_CAMS * 6 + tid];
-        if (tid == 0) {
-            misc->ci64 = reinterpret_cast<unsigned long long*>(A.out.bev_ci) + (size_t)sample * ncell;
-            misc->h32 = reinterpret_cast<int*>(A.out.bev_height) + (size_t)sample * ncell;
-        }
         __syncthreads();
 
         // ---- tile cursor: this part owns local tiles [lr0, lr1) of the sample, warp `warp` takes lr0 + warp, + W, ...; a tile is 128
@@ -573,13 +567,11 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             // ---- phase B: filter, BEV cell, cull entry, count word
             uint32_t cand[PPT], code[PPT];
             bool rare = false;
-            unsigned long long* ci64g;
-            int* h32g;
-            {
-                const uint2 a = s4_lds64(misc_s + (uint32_t)offsetof(S4Misc, ci64)), b = s4_lds64(misc_s + (uint32_t)offsetof(S4Misc, h32));
-                ci64g = reinterpret_cast<unsigned long long*>(((unsigned long long)a.y << 32) | a.x);
-                h32g = reinterpret_cast<int*>(((unsigned long long)b.y << 32) | b.x);
-            }
+            // this sample's (count, isum) layer as 64-bit cells and its max-height layer: re-derived from the sample index per tile (two
+            // wide multiply-adds; holding the two pointers would cost four of the 64 registers, reading them back from smem LSU wavefronts)
+            const unsigned long long cell0 = (unsigned long long)(uint32_t)sample * (unsigned long long)(uint32_t)(res * res);
+            unsigned long long* const ci64g = reinterpret_cast<unsigned long long*>(A.out.bev_ci) + cell0;
+            int* const h32g = reinterpret_cast<int*>(A.out.bev_height) + cell0;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
                 // lidar_agent.py:106-110, sqrt-free (thresholds on s are exact, geometry.sqrt_thresholds)
