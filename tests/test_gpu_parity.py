@@ -247,6 +247,32 @@ def test_fused_static_partition_over_ctas(engine):
         _capi.set_option("config", _capi.DEFAULT_FUSED_CONFIG)
 
 
+def test_fused_stream4_random_shapes_and_options(engine):
+    """stream4.cu against the oracle on random batch shapes crossed with random launch options: points per lane (1024 x 2 / 512 x 4),
+    grid (how samples straddle CTAs), window size, cull-cell size, the compile-time-constant instantiation on / off, grid geometry."""
+    rng = np.random.default_rng(2024)
+    try:
+        for trial in range(8):
+            n = int(rng.integers(1, 5))
+            s = [make_sample(int(rng.integers(300, 400)), n_sweeps=int(rng.integers(1, 6)), n_boxes=int(rng.integers(0, 90))) for _ in range(n)]
+            for smp in s:  # ragged sweeps: lengths that leave partial warp tiles of either shape
+                for sw in smp["lidar_sweeps"]:
+                    sw["points_raw"] = sw["points_raw"][: int(rng.integers(1, 34720))]
+            params = None
+            if trial % 3 == 2:
+                params = GeomParams(range_max=float(rng.choice([30.0, 40.0, 50.0])), bev_range=float(rng.choice([32.0, 51.2, 60.0])),
+                                    bev_res=int(rng.choice([64, 128, 256])), z_max=3.0, ground_z=-1.2)
+            _capi.set_option("ppt", int(rng.choice([2, 4])))
+            _capi.set_option("grid", int(rng.choice([0, 1, 3, 29, 148])))
+            _capi.set_option("window", int(rng.choice([0, 0, 16, 60])))
+            _capi.set_option("cull_shift", int(rng.choice([-1, -1, 1, 3])))
+            _capi.set_option("standard", int(rng.integers(0, 2)))
+            check_fused(engine, s, params=params, config=10)
+    finally:
+        for k, v in (("ppt", _capi.DEFAULT_FUSED_PPT), ("grid", 0), ("window", 0), ("cull_shift", -1), ("standard", 1), ("config", _capi.DEFAULT_FUSED_CONFIG)):
+            _capi.set_option(k, v)
+
+
 @pytest.mark.parametrize("config", [10, 7])
 def test_fused_full_size_batch_properties(engine, config):
     """BASELINE config-3 batch at the benchmark's size (592 samples, 205.5 M points): size-independent properties, replica
