@@ -1,6 +1,6 @@
-// fused_stream.cu -- second generation of the streaming kernel (launch shape "config" 7).  Superseded as the default by stream3.cu
-// (config 9); it still serves fov_keep_mask != 0 (a FOV *filter* needs the per-point wedge classes before the BEV update) and is the
-// shape every change to stream3.cu is compared with bit for bit (tools/sweep_configs.py).
+// fused_stream.cu -- second generation of the streaming kernel (launch shape "config" 7).  Superseded as the default by stream4.cu
+// (config 10); it still serves fov_keep_mask != 0 (a FOV *filter* needs the per-point wedge classes before the BEV update) and is the
+// shape every change to stream4.cu is compared with bit for bit (tools/sweep_configs.py).
 //
 // Same arithmetic, per point, as fused_evidence.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); what
 // changed is the control structure, because the first generation was instruction-issue bound (ncu: 80 % of issue

@@ -1,23 +1,27 @@
 // stream4.cu -- fourth generation of the streaming kernel (launch shape "config" 10, the default).
 //
-// Same arithmetic per point as stream3.cu / fused_stream.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); results are
-// bit-identical (tools/sweep_configs.py).  What changed, and why (gpurun_out/r2_s3d: stream3.cu issues 570 warp instructions per 64
-// points at 80 % issue-slot utilisation and 112 shared-memory wavefronts per 64 points at 74 % of the LSU data pipe -- both pipes have
-// to lose about half their work before HBM matters):
-//   * NO shared-memory ring, no TMA, no mbarriers: a lane owns FOUR consecutive raw rows (80 bytes, 16-byte aligned because every
-//     sweep starts at a multiple of 4 rows) and reads them with five coalesced 128-bit loads straight into registers, one tile (128
-//     rows per warp) ahead of their use.  That removes the per-tile bulk-copy issue / wait / cursor code (~65 instructions per 64
-//     points), the four LDS per point, and gives 80 KB of shared memory back to the BEV window.
-//   * 512 threads x 128 registers, four points per lane: per-tile overhead and the pose rows are amortised over 128 points, table
-//     bases and thresholds stay in registers instead of being re-read from the constant bank.
+// Same arithmetic per point as fused_stream.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); results are bit-identical
+// (tools/sweep_configs.py).  Every variant of this kernel saturates two units together: instruction issue and the LSU data pipe
+// (shared-memory wavefronts).  What this generation does about both, and about batches that do not fill the device:
+//   * work is partitioned STATICALLY in warp tiles (64 rows of one sweep): fused_tables_kernel prefix-sums the tiles of every sample,
+//     CTA b of G owns global tiles [b * total / G, (b + 1) * total / G).  A sample that straddles CTA boundaries (a single keyframe,
+//     a shard that is not a multiple of the SM count) is processed in parts that merge with integer reductions; the part that takes
+//     the last ticket finalises the sample.  Every SM gets the same share of the points whatever the batch size.
+//   * raw rows reach shared memory through a per-warp TMA ring (cp.async.bulk on the warp's own mbarriers): the bulk copy costs the
+//     LSU data pipe nothing.  (Measured alternative, commit b7fc82f: rows straight into registers with 128-bit loads -- fewer
+//     instructions, no ring, and slower: the strided loads re-touch every 128-byte line five times on that pipe.)
 //   * dropped points are counted by WHERE their atomic lands (one sink word per lane for remove_close, another for the range /
 //     height gate), periphery points count into their cull cell's word (which returns the cell's edge code like a window word does):
 //     n_after_close, n_kept and the decided share of the per-camera counts all come out of the epilogue's sums.
-//   * cull-cell ids and classes are separate 4-byte tables (the hot loop only reads the ids: half the bank conflicts).
-//   * work is partitioned STATICALLY in warp tiles: a pre-kernel prefix-sums the tiles of every sample, CTA b of G owns global tiles
-//     [b * total / G, (b + 1) * total / G).  A sample that straddles CTA boundaries (a single keyframe, a shard that is not a
-//     multiple of the SM count) is processed in parts that merge with integer reductions; the part that takes the last ticket
-//     finalises the sample.  Every SM gets the same share of the points whatever the batch size.
+//   * the edge code a count word returns selects ONE branch-free cross product; cells crossed by exactly two rays of different
+//     cameras get pair codes (assigned per sample as they occur) and a second test under a warp vote; anything else is a cold path.
+//   * cull-cell ids are a 4-byte table of their own; class words live in a per-CTA slice of the workspace (the hot loop never reads
+//     them); window rows have an odd stride (a ray along y does not pile up in one bank).
+//   * the shared-memory layout is a constexpr function used by the host and by the kernel: the instantiation for the standard
+//     configuration (STD) takes every offset and threshold as a compile-time constant instead of re-reading the constant bank and
+//     re-deriving table addresses per tile (at 64 registers per thread nothing of that survives in registers).
+//   * the result tables of a shard can be REPLICATED to the other GPUs of the box by the finalising code itself (P2P stores through
+//     A.replica[]): the gather of a sharded batch without a collective.
 #include "fused_common.cuh"
 
 namespace msc {
