@@ -47,7 +47,7 @@ struct S4Misc {  // small per-CTA state at misc_off
     // [code]: 0 = pad (the test fails: a = NaN); 1 + c right edge, 9 + c left edge of camera c; 17 + i the first / second edge of pair i
     // (edge2 is a pad for every other code); 31 = several edges, resolved on a cold path from the cell's class word
     S4Edge edge1[32], edge2[32];
-    uint32_t inc1[32], inc2[32];  // nibble-counter increment of the entry's camera (1 << 4 c): one word per entry, 32 entries = 32 banks
+    uint2 inc1[32], inc2[32];  // byte-counter increments (cameras 0-3, 4-7) of the entry's camera
     uint32_t pairs[16];  // pair i: 0 = free, else 0x100 | e1 | e2 << 4 (edge numbers 0-7 right, 8-15 left)
     uint32_t stats[MSC_STATS_STRIDE];
     uint32_t sweep_start[kS4PoseSmem], sweep_count[kS4PoseSmem];
@@ -419,14 +419,15 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             else if (code >= 17 && code < 17 + kS4PairCodes && misc->pairs[code - 17]) e = (int)((misc->pairs[code - 17] >> (second ? 4 : 0)) & 0xfu);
             S4Edge E;
             E.ax = 0.0f; E.ay = 0.0f; E.a = __int_as_float(0x7fc00000); E.b = 0.0f;  // pad: the test fails
-            uint32_t inc = 0u;
+            uint2 inc = make_uint2(0u, 0u);
             const int c = e & (MSC_MAX_CAMS - 1);
             if (FOV && e >= 0 && c < n_cams) {
                 const float* wq = misc->wq + c * 6;
                 // cr = fma(a, qy, -(b * qx)) >= 0 with (a, b) = (w4, w5) for a right edge, (-w2, -w3) for a left one  (in_wedge)
                 E.ax = wq[0]; E.ay = wq[1];
                 if (e >= MSC_MAX_CAMS) { E.a = -wq[2]; E.b = -wq[3]; } else { E.a = wq[4]; E.b = wq[5]; }
-                inc = 1u << (4 * c);
+                inc.x = c < 4 ? 1u << (8 * c) : 0u;
+                inc.y = c < 4 ? 0u : 1u << (8 * (c - 4));
             }
             (second ? misc->edge2 : misc->edge1)[code] = E;
             (second ? misc->inc2 : misc->inc1)[code] = inc;
@@ -435,8 +436,10 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
 
         // ------------------------------------------------------------ main loop: this warp's tiles, no cross-warp sync
         uint32_t c_ground = 0;             // per-thread counter (flushed once per sample)
-        uint32_t cam = 0;     // eight 4-bit per-camera counters of the exact edge tests (a point adds at most 1 per camera), spilled
-        uint32_t pstate = 0;  // into the sample's smem counters before 15 points have been added since the last spill
+        uint32_t cam_lo = 0, cam_hi = 0;  // eight 8-bit per-camera counters of the exact edge tests (a point adds at most 1 per camera),
+        uint32_t pstate = 0;              // spilled into the sample's smem counters before 255 points have been added since the last spill
+        // (measured alternative: 4-bit counters in one register with one-word increments -- three LSU wavefronts fewer per tile, a spill
+        // every 7 tiles instead of every 127: 0.4 % slower)
         uint32_t q_head = 0, q_tail = 0;   // warp-uniform (every lane derives them from the same ballots)
         // Every lane tests TWO queued points (entries head + lane and head + 32 + lane) against their candidate boxes, one candidate of
         // each per trip, so two independent box tests are in flight per lane; the (usually single) containing box is accumulated once
@@ -610,16 +613,16 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) {
                     const float4 E = s4_lds128(edge1_s + (code[u] << 4));
-                    const uint32_t inc = s4_lds32(edge1_s + kInc1 + (code[u] << 2));
+                    const uint2 inc = s4_lds64(edge1_s + kInc1 + (code[u] << 3));
                     const float qx = __fsub_rn(xr[u], E.x), qy = __fsub_rn(yr[u], E.y);
                     const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
-                    if (cr >= 0.0f) cam += inc;
+                    if (cr >= 0.0f) { cam_lo += inc.x; cam_hi += inc.y; }
                     if (__any_sync(0xffffffffu, code[u] > 2u * MSC_MAX_CAMS)) {
                         const float4 E2 = s4_lds128(edge1_s + kEdge2 + (code[u] << 4));
-                        const uint32_t inc2 = s4_lds32(edge1_s + kInc2 + (code[u] << 2));
+                        const uint2 inc2 = s4_lds64(edge1_s + kInc2 + (code[u] << 3));
                         const float qx2 = __fsub_rn(xr[u], E2.x), qy2 = __fsub_rn(yr[u], E2.y);
                         const float cr2 = __fmaf_rn(E2.z, qy2, -__fmul_rn(E2.w, qx2));
-                        if (cr2 >= 0.0f) cam += inc2;
+                        if (cr2 >= 0.0f) { cam_lo += inc2.x; cam_hi += inc2.y; }
                     }
                 }
                 if (__any_sync(0xffffffffu, rare)) {  // cold: cells crossed by three or more rays, or by both rays of one camera (next to a camera)
@@ -650,8 +653,8 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                         // cameras with an undecided edge in this cell whose every undecided edge passed
                         const uint32_t any_und = ((cls >> 8) | (cls >> 16)) & 0xffu;
                         const uint32_t in = cls & any_und & pass & (pass >> 8);
-#pragma unroll
-                        for (int c = 0; c < MSC_MAX_CAMS; ++c) cam += ((in >> c) & 1u) << (4 * c);  // bit c -> nibble c (cold)
+                        cam_lo += ((in & 0xfu) * 0x00204081u) & 0x01010101u;  // bit c -> byte c
+                        cam_hi += ((in >> 4) * 0x00204081u) & 0x01010101u;
                     }
                 }
             }
@@ -678,13 +681,13 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             }
             if (FOV) {
                 pstate += PPT;
-                if (pstate > 15u - PPT) {  // spill the nibble counters before any of them can wrap
+                if (pstate > 255u - PPT) {  // spill the byte counters before any of them can wrap
 #pragma unroll
                     for (int c = 0; c < MSC_MAX_CAMS; ++c) {
-                        const uint32_t v = (cam >> (4 * c)) & 0xfu;
+                        const uint32_t v = ((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu;
                         if (v) s4_red_add(misc_s + (uint32_t)offsetof(S4Misc, stats) + (uint32_t)(5 + c) * 4u, v);
                     }
-                    cam = pstate = 0;
+                    cam_lo = cam_hi = pstate = 0;
                 }
             }
         }
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
         // share of the per-camera counts.
         uint32_t kept = 0, removed = 0, flags = 0, camc[MSC_MAX_CAMS];
 #pragma unroll
-        for (int c = 0; c < MSC_MAX_CAMS; ++c) camc[c] = FOV ? ((cam >> (4 * c)) & 0xfu) : 0u;
+        for (int c = 0; c < MSC_MAX_CAMS; ++c) camc[c] = FOV ? (((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu) : 0u;
         if (tid < 32) removed = arrA[tid];
         for (int i = tid; i < n_cull; i += NT) {  // periphery points, per cull cell
             const uint32_t c0 = pcnt[i] & kS4CountMask;
