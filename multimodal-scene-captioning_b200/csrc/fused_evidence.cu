@@ -457,7 +457,7 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* para
         args.L = stream4_layout(X->smem_optin, X->opt_ppt, params->bev_res, cdim, cshift, cap, X->opt_window, inner);
         rc = args.L.win_w < 0 ? -1 : 0;
         standard = rc == 0 && fast && stream4_is_standard(args, X->smem_optin, X->opt_ppt, X->opt_window) && X->opt_std != 0;
-        X->last_tile_pts = 32 * X->opt_ppt; X->last_threads = stream4_threads(X->opt_ppt);
+        X->last_tile_pts = 128; X->last_threads = stream4_threads(X->opt_ppt);
     } else {
         int threads = 0, tile_pts = 0, ring = 0, queue = 0;
         stream_shape_info(&threads, &tile_pts, &ring, &queue);
@@ -471,14 +471,14 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* para
     X->last_config = gen;
     X->last_window = args.L.win_w;
     X->last_smem = args.L.total_bytes;
-    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, gen == 10 ? 32 * X->opt_ppt : 0, stream)) != MSC_OK) return rc;
+    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, gen == 10 ? 128 : 0, stream)) != MSC_OK) return rc;  // stream4.cu: 128-row warp tiles
     int grid;
     if (gen == 10) {
         // every CTA gets the same number of warp tiles; a batch of a few thousand rows is not spread thinner than one tile per warp
         const long long pts = in->points_per_sample_hint > 0 ? in->points_per_sample_hint : 347200;
-        const int tile_pts = 32 * X->opt_ppt, warps = stream4_threads(X->opt_ppt) / 32;
+        const int tile_pts = 128, warps = stream4_threads(X->opt_ppt) / 32;
         const long long est_tiles = (long long)in->n_samples * ((pts + tile_pts - 1) / tile_pts);
-        long long g = X->opt_grid > 0 ? X->opt_grid : est_tiles / warps;
+        long long g = X->opt_grid > 0 ? X->opt_grid : 2 * est_tiles / warps;  // (small batches: down to half a tile per warp)
         grid = (int)(g < 1 ? 1 : (g > X->sms ? X->sms : g));
         if (grid > kMaxGrid) grid = kMaxGrid;
         if ((rc = launch_stream4_partition(args, T, ws, grid, stream, &X->last_launches)) != MSC_OK) return rc;

@@ -66,7 +66,8 @@ int stream4_threads(int ppt) { return s4_threads(ppt); }
 // and, last, the box tables (their size is the only part that depends on the batch).  constexpr: the kernel instantiation for the
 // standard configuration takes every offset from here as a compile-time constant (immediate operands instead of constant-bank loads
 // and address arithmetic), the host uses the same function for every configuration.
-__host__ __device__ constexpr int s4_warp_block_bytes(int ppt) { return 2 * 32 * ppt * 20 + s4_queue_entries(ppt) * 16 + 16; }  // (a multiple of 16)
+constexpr int kS4TileRows = 128;  // rows of a warp tile for both launch shapes: one bulk copy, one wait, one cursor step per 128 rows
+__host__ __device__ constexpr int s4_warp_block_bytes(int ppt) { return kS4TileRows * 20 + s4_queue_entries(ppt) * 16 + 16; }  // (a multiple of 16)
 __host__ __device__ constexpr FusedLayout s4_layout(int smem_bytes, int ppt, int res, int cull_dim, int cull_shift, int box_cap, int opt_window,
                                                     int inner_dim) {
     FusedLayout L{};
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) stream4_straddle_kernel(const __grid_cons
 template <bool FOV, bool FASTDIV, int PPT, bool STD>
 __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __grid_constant__ FusedArgs A, const TableLayout T,
                                                                      unsigned char* __restrict__ ws) {
-    constexpr int NT = s4_threads(PPT), W = NT / 32, TP = 32 * PPT, TSH = PPT == 4 ? 7 : 6, kS4QueueEntries = s4_queue_entries(PPT);
+    constexpr int NT = s4_threads(PPT), W = NT / 32, TP = kS4TileRows, TSH = 7, SUB = kS4TileRows / (32 * PPT), kS4QueueEntries = s4_queue_entries(PPT);
     extern __shared__ __align__(128) unsigned char smem[];
     // STD: every layout offset and every threshold of the main loop is a compile-time constant (the host selects this instantiation only
     // when the call's layout and parameters equal them bit for bit, stream4_is_standard); otherwise they are kernel arguments
@@ -252,9 +253,9 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     asm volatile("" : "+r"(smem_s));  // opaque: one live register instead of a re-derived generic->shared conversion per use
     const uint32_t misc_s = smem_s + (uint32_t)L.misc_off;
     constexpr uint32_t kSlotBytes = (uint32_t)TP * 20u, kWarpBlock = (uint32_t)s4_warp_block_bytes(PPT);
-    const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * kWarpBlock;  // this warp's block: two slots of raw rows,
-    const uint32_t queue_s = ring_s + 2u * kSlotBytes;                                     // its candidate queue
-    const uint32_t bar_s = queue_s + (uint32_t)(kS4QueueEntries * 16);                     // and its two mbarriers
+    const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * kWarpBlock;  // this warp's block: ONE slot of 128 raw rows,
+    const uint32_t queue_s = ring_s + kSlotBytes;                                          // its candidate queue
+    const uint32_t bar_s = queue_s + (uint32_t)(kS4QueueEntries * 16);                     // and its mbarrier
     const uint64_t policy = l2_policy_evict_first();
     const uint32_t edge1_s = misc_s + (uint32_t)offsetof(S4Misc, edge1);
     constexpr uint32_t kEdge2 = (uint32_t)(offsetof(S4Misc, edge2) - offsetof(S4Misc, edge1)), kInc1 = (uint32_t)(offsetof(S4Misc, inc1) - offsetof(S4Misc, edge1)),
@@ -272,10 +273,9 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
 
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8u), "r"(1) : "memory");
         mbar_fence_init();
     }
-    uint32_t wk = 0;  // tiles this warp has consumed since launch: slot = wk & 1, mbarrier parity = (wk >> 1) & 1
+    uint32_t wk = 0;  // tiles this warp has consumed since launch: mbarrier parity = wk & 1
     __syncthreads();
 
     // ------------------------------------------------------------ this CTA's share of the batch: a range of global tiles
@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             lr0 = max(g0, off) - off;
             lr1 = min(g1, off + tiles_s) - off;
             if (lr0 >= lr1) continue;
-            n_parts = cta_of(off + tiles_s - 1u) - cta_of(off) + 1u;
+            // CTAs that own at least one tile of the sample.  With at least one tile per CTA the owners are contiguous; with fewer tiles
+            // than CTAs every tile has an owner of its own (and the CTAs in between own nothing)
+            n_parts = total >= G ? cta_of(off + tiles_s - 1u) - cta_of(off) + 1u : tiles_s;
         }
         __syncthreads();  // the previous sample's epilogue has read the per-CTA state that is re-initialised below
 
@@ -332,23 +334,25 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
         };
         // Raw rows travel global -> shared memory with the TMA unit (cp.async.bulk, completion on the warp's own mbarrier): the copy
         // costs the LSU data pipe nothing -- five strided 64/128-bit loads per lane re-touch every 128-byte line five times there, and that
-        // pipe is what the kernel saturates first -- and no registers.  Two slots per warp: the successor of the tile being processed.
-        auto issue = [&](uint32_t slot) {  // whole warp (uniform control flow); one lane talks to the TMA unit
+        // pipe is what the kernel saturates first -- and no registers.  ONE slot of 128 rows per warp: the lanes read the slot in SUB
+        // passes of 32 * PPT rows; as soon as the last pass has read its rows the slot is free and the next tile's copy goes out, so it
+        // has the whole last pass (>= half a tile of work) to land.  One copy, one wait and one cursor step per 128 rows.
+        auto issue = [&]() {  // whole warp (uniform control flow); one lane talks to the TMA unit
             const uint32_t first = (t - s_tb) << TSH;
             const uint32_t npts = min((uint32_t)TP, s_cnt - first);
             const uint32_t bytes = (npts * 20u + 15u) & ~15u;
             const float* src = A.in.points + ((size_t)s_base + first) * 5;
             if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + slot * 8u), "r"(bytes) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                        ring_s + slot * kSlotBytes),
-                    "l"(src), "r"(bytes), "r"(bar_s + slot * 8u), "l"(policy)
+                        ring_s),
+                    "l"(src), "r"(bytes), "r"(bar_s), "l"(policy)
                     : "memory");
             }
         };
         bool more = t < lr1;
-        if (more) { seek_sweep(); issue(wk & 1u); }  // overlaps the prologue below
+        if (more) { seek_sweep(); issue(); }  // overlaps the prologue below
 
         // ------------------------------------------------------------ prologue: accumulators, tables -> smem
         const int bx0 = A.in.sample_box_off[sample];
@@ -508,13 +512,10 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 __syncwarp();
                 pose_s = misc_s + (uint32_t)offsetof(S4Misc, wpose) + (uint32_t)warp * 96u;
             }
-            // ---- the tile in flight becomes the current one; its successor takes the slot consumed in the previous iteration
+            // ---- the tile in flight becomes the current one
             const uint32_t npts = min((uint32_t)TP, s_cnt - ((t - s_tb) << TSH));
-            t += (uint32_t)W;
-            more = t < lr1;
-            if (more) { seek_sweep(); issue((wk + 1u) & 1u); }
             {
-                const uint32_t bar = bar_s + (wk & 1u) * 8u, parity = (wk >> 1) & 1u;
+                const uint32_t bar = bar_s, parity = wk & 1u;
                 asm volatile(
                     "{\n"
                     ".reg .pred p;\n"
@@ -527,6 +528,8 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     "r"(parity)
                     : "memory");
             }
+#pragma unroll 1
+          for (int sub = 0; sub < SUB; ++sub) {  // SUB passes of 32 * PPT rows over the slot
             // ---- phase A: branch-free over the lane's points so their dependency chains interleave.  Lane l owns rows l, l + 32, ... of
             // the tile (a 5-word stride between lanes: bank-conflict free, and the 32 lanes of a slot hold 32 different rings)
             float xr[PPT], yr[PPT], zr[PPT];
@@ -534,16 +537,15 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             bool close[PPT];
             {
                 double xd[PPT], yd[PPT], zd[PPT];
-                const uint32_t row_s = ring_s + (wk & 1u) * kSlotBytes + (uint32_t)lane * 20u;
+                const uint32_t row_s = ring_s + (uint32_t)sub * (uint32_t)(PPT * 640) + (uint32_t)lane * 20u;
                 const bool partial = npts < (uint32_t)TP;  // (warp-uniform)
-                ++wk;
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) {
                     float x = __uint_as_float(s4_lds32(row_s + u * 640u));
                     const float y = __uint_as_float(s4_lds32(row_s + u * 640u + 4u)), z = __uint_as_float(s4_lds32(row_s + u * 640u + 8u));
                     const float inten = __uint_as_float(s4_lds32(row_s + u * 640u + 12u));
                     // last tile of a sweep: rows past its end hold stale data -> NaN fails every compare below
-                    if (partial && (uint32_t)lane + (uint32_t)u * 32u >= npts) x = __int_as_float(0x7fc00000);
+                    if (partial && (uint32_t)lane + (uint32_t)(u + sub * PPT) * 32u >= npts) x = __int_as_float(0x7fc00000);
                     // A.1 remove_close (square, sweep's own sensor frame)
                     close[u] = (fabsf(x) < P.remove_close_radius) & (fabsf(y) < P.remove_close_radius);
                     // Q8 intensity, clamp [0, 65535], NaN -> 0: fmaxf drops NaN and negatives, the FFMA rounds v * 2^shift to nearest even
@@ -551,7 +553,13 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     q[u] = min(__float_as_uint(__fmaf_rn(fmaxf(inten, 0.0f), iscale, 8388608.0f)) - 0x4b000000u, 65535u);
                     xd[u] = (double)x; yd[u] = (double)y; zd[u] = (double)z;
                 }
-                __syncwarp();  // every lane has read its rows: the slot may be refilled at the top of the next iteration
+                if (sub == SUB - 1) {  // every row of the slot has been read: the successor's copy goes out now
+                    __syncwarp();
+                    ++wk;
+                    t += (uint32_t)W;
+                    more = t < lr1;
+                    if (more) { seek_sweep(); issue(); }
+                }
                 // A.1 f64 matrix x f32 point -> f32, one matrix row at a time
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
@@ -690,6 +698,7 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     cam_lo = cam_hi = pstate = 0;
                 }
             }
+          }
         }
         while (q_tail != q_head) {
             __syncwarp();

@@ -237,6 +237,11 @@ def test_fused_static_partition_over_ctas(engine):
             _capi.set_option("grid", grid)
             check_fused(engine, [empty, s[0], empty, empty, s[3], empty], config=10)
             check_fused(engine, [empty, empty], config=10)
+        tiny = make_sample(91, n_sweeps=1, n_boxes=19)                    # fewer warp tiles (87) than CTAs: most CTAs own nothing,
+        tiny["lidar_sweeps"][0]["points_raw"] = tiny["lidar_sweeps"][0]["points_raw"][:11029]   # every tile is a part of its own
+        for grid in (148, 100, 87, 86):
+            _capi.set_option("grid", grid)
+            check_fused(engine, [tiny], config=10)
         _capi.set_option("window", 20)                                    # most cells through the global reductions, partitioned as well
         _capi.set_option("grid", 11)
         check_fused(engine, s, config=10)
