@@ -3,18 +3,23 @@
 // Same arithmetic per point as fused_stream.cu (SURVEY.md App. A + lidar_agent.py:103-132, :547-560); results are bit-identical
 // (tools/sweep_configs.py).  Every variant of this kernel saturates two units together: instruction issue and the LSU data pipe
 // (shared-memory wavefronts).  What this generation does about both, and about batches that do not fill the device:
-//   * work is partitioned STATICALLY in warp tiles (64 rows of one sweep): fused_tables_kernel prefix-sums the tiles of every sample,
+//   * work is partitioned STATICALLY in warp tiles (128 rows of one sweep): fused_tables_kernel prefix-sums the tiles of every sample,
 //     CTA b of G owns global tiles [b * total / G, (b + 1) * total / G).  A sample that straddles CTA boundaries (a single keyframe,
 //     a shard that is not a multiple of the SM count) is processed in parts that merge with integer reductions; the part that takes
 //     the last ticket finalises the sample.  Every SM gets the same share of the points whatever the batch size.
-//   * raw rows reach shared memory through a per-warp TMA ring (cp.async.bulk on the warp's own mbarriers): the bulk copy costs the
-//     LSU data pipe nothing.  (Measured alternative, commit b7fc82f: rows straight into registers with 128-bit loads -- fewer
-//     instructions, no ring, and slower: the strided loads re-touch every 128-byte line five times on that pipe.)
+//   * raw rows reach shared memory through the TMA unit (cp.async.bulk into the warp's own tile slot, completion on the warp's own
+//     mbarrier): the bulk copy costs the LSU data pipe nothing.  The lanes read the slot in passes of 32 * PPT rows; the next tile's
+//     copy is issued as soon as the last pass has its rows in registers.  (Measured alternatives: two 64-row slots with two mbarriers,
+//     4.6 % slower; commit b7fc82f, rows straight into registers with 128-bit loads -- fewer instructions, no slot, and slower: the
+//     strided loads re-touch every 128-byte line five times on that pipe.)
 //   * dropped points are counted by WHERE their atomic lands (one sink word per lane for remove_close, another for the range /
 //     height gate), periphery points count into their cull cell's word (which returns the cell's edge code like a window word does):
 //     n_after_close, n_kept and the decided share of the per-camera counts all come out of the epilogue's sums.
-//   * the edge code a count word returns selects ONE branch-free cross product; cells crossed by exactly two rays of different
-//     cameras get pair codes (assigned per sample as they occur) and a second test under a warp vote; anything else is a cold path.
+//   * the edge code a count word returns says whether an image-column ray crosses the point's cell at all (19 % of the kept points);
+//     those points wait in a per-warp edge queue and are tested 32 at a time, one per lane: ONE branch-free cross product selected by
+//     the code; cells crossed by exactly two rays of different cameras get pair codes (assigned per sample as they occur) and a
+//     second test under a warp vote; anything else is a cold path.  (Testing every point in line -- a pad entry for code 0 -- issued
+//     the same number of instructions but 6 % more shared-memory wavefronts.)
 //   * cull-cell ids are a 4-byte table of their own; class words live in a per-CTA slice of the workspace (the hot loop never reads
 //     them); window rows have an odd stride (a ray along y does not pile up in one bank).
 //   * the shared-memory layout is a constexpr function used by the host and by the kernel: the instantiation for the standard
@@ -26,14 +31,14 @@
 
 namespace msc {
 
-// Two launch shapes: PPT = 4 points per lane (512 threads x 128 registers, 128-row warp tiles read with 128-bit loads) and PPT = 2
-// (768 threads x 80 registers, 64-row warp tiles read with 64-bit loads: more warps to hide latency, less amortisation per tile).
+// Two launch shapes: PPT = 2 points per lane and pass (1024 threads x 64 registers, the default: more warps to hide latency) and PPT = 4
+// (512 threads x 128 registers: fewer instructions per point, half the warps).
 __host__ __device__ constexpr int s4_threads(int ppt) { return ppt == 4 ? 512 : 1024; }
 constexpr int kS4MaxWarps = 32;
 // candidate queue per warp.  PPT = 4: 128 entries, drained 64 at a time (two per lane), checked every two point slots (<= 63 pending + 64
 // pushed); PPT = 2: 64 entries, drained 32 at a time, checked after every point slot (<= 31 pending + 32 pushed)
 __host__ __device__ constexpr int s4_queue_entries(int ppt) { return ppt == 4 ? 128 : 64; }
-constexpr int kS4PoseSmem = 12;   // sweeps whose transforms / extents are staged per sample; later ones are read from global memory
+constexpr int kS4PoseSmem = 10;   // sweeps whose transforms / extents are staged per sample (BASELINE configs 3-5: 10); later ones are read from global memory
 constexpr int kS4SinkWords = 64;  // per array: [0, 32) remove_close sink of lane l, [32, 64) range / height sink of lane l
 constexpr uint32_t kS4CodeShift = 27, kS4CountMask = (1u << kS4CodeShift) - 1u, kS4CodeMulti = 31u;
 
@@ -59,15 +64,20 @@ struct S4Misc {  // small per-CTA state at misc_off
 
 int stream4_threads(int ppt) { return s4_threads(ppt); }
 
-// Shared-memory layout (bytes).  One block per warp first -- its two ring slots of raw rows, its candidate queue, its two mbarriers: one
-// base register reaches all of them with immediate offsets -- then the cull-cell ids, the small per-CTA state, the window region
+// Shared-memory layout (bytes).  One block per warp first -- its tile slot of raw rows, its candidate queue, its edge queue, its mbarrier:
+// one base register reaches all of them with immediate offsets -- then the cull-cell ids, the small per-CTA state, the window region
 //   array A = [64 sink words][win_w^2 count | code << 27][cull_dim^2 periphery count | code << 27]
 //   array B = [64 sink words][win_w^2 Q8 intensity sums]
 // and, last, the box tables (their size is the only part that depends on the batch).  constexpr: the kernel instantiation for the
 // standard configuration takes every offset from here as a compile-time constant (immediate operands instead of constant-bank loads
 // and address arithmetic), the host uses the same function for every configuration.
 constexpr int kS4TileRows = 128;  // rows of a warp tile for both launch shapes: one bulk copy, one wait, one cursor step per 128 rows
-__host__ __device__ constexpr int s4_warp_block_bytes(int ppt) { return kS4TileRows * 20 + s4_queue_entries(ppt) * 16 + 16; }  // (a multiple of 16)
+// edge queue per warp: points of cells that an image-column ray crosses wait here (x, y: 8 bytes; the cell's edge code: 1 byte) until 32
+// are pending, then every lane runs the exact cross products of one of them.  Checked after every point slot (<= 31 pending + 32 pushed)
+constexpr int kS4EdgeEntries = 64;
+__host__ __device__ constexpr int s4_warp_block_bytes(int ppt) {  // (a multiple of 16)
+    return kS4TileRows * 20 + s4_queue_entries(ppt) * 16 + kS4EdgeEntries * 8 + kS4EdgeEntries + 16;
+}
 __host__ __device__ constexpr FusedLayout s4_layout(int smem_bytes, int ppt, int res, int cull_dim, int cull_shift, int box_cap, int opt_window,
                                                     int inner_dim) {
     FusedLayout L{};
@@ -137,6 +147,11 @@ __device__ __forceinline__ float4 s4_lds128(uint32_t saddr) {
 __device__ __forceinline__ uint2 s4_lds64(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t s4_lds8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ uint32_t s4_lds32(uint32_t saddr) {
@@ -255,7 +270,9 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
     constexpr uint32_t kSlotBytes = (uint32_t)TP * 20u, kWarpBlock = (uint32_t)s4_warp_block_bytes(PPT);
     const uint32_t ring_s = smem_s + (uint32_t)L.tiles_off + (uint32_t)warp * kWarpBlock;  // this warp's block: ONE slot of 128 raw rows,
     const uint32_t queue_s = ring_s + kSlotBytes;                                          // its candidate queue
-    const uint32_t bar_s = queue_s + (uint32_t)(kS4QueueEntries * 16);                     // and its mbarrier
+    const uint32_t eq_s = queue_s + (uint32_t)(kS4QueueEntries * 16);                      // its edge queue: (x, y) pairs,
+    const uint32_t eqc_s = eq_s + (uint32_t)(kS4EdgeEntries * 8);                          // their edge codes (bytes)
+    const uint32_t bar_s = eqc_s + (uint32_t)kS4EdgeEntries;                               // and its mbarrier
     const uint64_t policy = l2_policy_evict_first();
     const uint32_t edge1_s = misc_s + (uint32_t)offsetof(S4Misc, edge1);
     constexpr uint32_t kEdge2 = (uint32_t)(offsetof(S4Misc, edge2) - offsetof(S4Misc, edge1)), kInc1 = (uint32_t)(offsetof(S4Misc, inc1) - offsetof(S4Misc, edge1)),
@@ -502,6 +519,63 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             if (hit1 >= 0) accumulate(hit1, e1);
             q_head += n_take;
         };
+        // ---- exact cross products for the points of cells that image-column rays cross, 32 queued points at a time (one per lane): the
+        // first ray of the point's edge code for every lane (a pad entry's test fails), the second ray (codes 17..30) and the cold path
+        // (code 31: cells crossed by three or more rays, or by both rays of one camera, next to a camera) under warp votes.  The camera's
+        // byte counter takes the entry's increment: at most one per camera and call.
+        uint32_t e_head = 0, e_tail = 0;  // warp-uniform
+        auto drain_edges = [&](uint32_t n_take) {  // n_take <= 32
+            const uint32_t slot = (e_head + (uint32_t)lane) & (uint32_t)(kS4EdgeEntries - 1);
+            const uint2 pw = s4_lds64(eq_s + (slot << 3));
+            const float px = __uint_as_float(pw.x), py = __uint_as_float(pw.y);
+            const uint32_t code = (uint32_t)lane < n_take ? s4_lds8(eqc_s + slot) : 0u;
+            {
+                const float4 E = s4_lds128(edge1_s + (code << 4));
+                const uint2 inc = s4_lds64(edge1_s + kInc1 + (code << 3));
+                const float qx = __fsub_rn(px, E.x), qy = __fsub_rn(py, E.y);
+                const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
+                if (cr >= 0.0f) { cam_lo += inc.x; cam_hi += inc.y; }
+            }
+            if (__any_sync(0xffffffffu, code > 2u * MSC_MAX_CAMS)) {
+                const float4 E2 = s4_lds128(edge1_s + kEdge2 + (code << 4));
+                const uint2 inc2 = s4_lds64(edge1_s + kInc2 + (code << 3));
+                const float qx2 = __fsub_rn(px, E2.x), qy2 = __fsub_rn(py, E2.y);
+                const float cr2 = __fmaf_rn(E2.z, qy2, -__fmul_rn(E2.w, qx2));
+                if (cr2 >= 0.0f) { cam_lo += inc2.x; cam_hi += inc2.y; }
+            }
+            if (__any_sync(0xffffffffu, code == kS4CodeMulti)) {
+                if (code == kS4CodeMulti) {
+                    // the class the point's code came from: its cull cell's outside the window, else its BEV cell's
+                    uint32_t cix, ciy;
+                    s4_bev_cell_xy<FASTDIV>(px, py, P.bev_range, two_r, rcp_two_r, resf, (uint32_t)res_m1, cix, ciy);
+                    const bool pp = max(cix - (uint32_t)win_lo, ciy - (uint32_t)win_lo) >= (uint32_t)win_w;
+                    const uint32_t cls = pp ? cullcls[(ciy >> L.cull_shift) * L.cull_dim + (cix >> L.cull_shift)] : class_of((int)cix, (int)ciy);
+                    uint32_t und = (cls >> 8) & 0xffffu, pass = 0xffffu;
+                    while (und) {
+                        const int e = __ffs((int)und) - 1;
+                        und &= und - 1u;
+                        const float4 E = s4_lds128(edge1_s + ((uint32_t)(e + 1) << 4));
+                        const float qx = __fsub_rn(px, E.x), qy = __fsub_rn(py, E.y);
+                        const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
+                        if (!(cr >= 0.0f)) pass &= ~(1u << e);
+                    }
+                    // cameras with an undecided edge in this cell whose every undecided edge passed
+                    const uint32_t any_und = ((cls >> 8) | (cls >> 16)) & 0xffu;
+                    const uint32_t in = cls & any_und & pass & (pass >> 8);
+                    cam_lo += ((in & 0xfu) * 0x00204081u) & 0x01010101u;  // bit c -> byte c
+                    cam_hi += ((in >> 4) * 0x00204081u) & 0x01010101u;
+                }
+            }
+            e_head += n_take;
+            if (++pstate == 255u) {  // spill the byte counters before any of them can wrap
+#pragma unroll
+                for (int c = 0; c < MSC_MAX_CAMS; ++c) {
+                    const uint32_t v = ((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu;
+                    if (v) s4_red_add(misc_s + (uint32_t)offsetof(S4Misc, stats) + (uint32_t)(5 + c) * 4u, v);
+                }
+                cam_lo = cam_hi = pstate = 0;
+            }
+        };
         while (more) {
             // the transform of the tile that is consumed now (n_si is still its sweep: the cursor advances further down); recomputed per
             // tile rather than carried in registers
@@ -580,7 +654,6 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
             }
             // ---- phase B: filter, BEV cell, cull entry, count word
             uint32_t cand[PPT], code[PPT];
-            bool rare = false;
             // this sample's (count, isum) layer as 64-bit cells and its max-height layer: re-derived from the sample index per tile (two
             // wide multiply-adds; holding the two pointers would cost four of the 64 registers, reading them back from smem LSU wavefronts)
             const unsigned long long cell0 = (unsigned long long)(uint32_t)sample * (unsigned long long)(uint32_t)(res * res);
@@ -607,75 +680,36 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                 if (keep && zr[u] < P.ground_z) ++c_ground;  // lidar_agent.py:128
                 code[u] = old >> kS4CodeShift;
                 cand[u] = keep ? ids : kCullEmpty;
-                rare = rare || (code[u] == kS4CodeMulti);
                 // cells outside the window take one 64-bit reduction on the global (count, isum) cell, the max-height layer one on the float
                 // bits for z > 0 (lidar_agent.py:560, 0-initialised max); both predicated, no branch
                 const uint32_t lin = iy * (uint32_t)res + ix;
                 s4_red_global_u64_if(ci64g + lin, 1ull | ((unsigned long long)q[u] << 32), keep && !inwin);
                 s4_red_global_max_if(h32g + lin, __float_as_int(zr[u]), keep && zr[u] > 0.0f);
             }
-            // ---- phase F: exact cross products for the points of cells that image-column rays cross.  Branch-free for the first ray (every
-            // other point reads a pad entry whose test fails); the camera's byte counter takes the entry's increment.  A second ray
-            // (codes 17..30: ~3 % of the points) is tested under a warp vote.
-            if (FOV) {
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const float4 E = s4_lds128(edge1_s + (code[u] << 4));
-                    const uint2 inc = s4_lds64(edge1_s + kInc1 + (code[u] << 3));
-                    const float qx = __fsub_rn(xr[u], E.x), qy = __fsub_rn(yr[u], E.y);
-                    const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
-                    if (cr >= 0.0f) { cam_lo += inc.x; cam_hi += inc.y; }
-                    if (__any_sync(0xffffffffu, code[u] > 2u * MSC_MAX_CAMS)) {
-                        const float4 E2 = s4_lds128(edge1_s + kEdge2 + (code[u] << 4));
-                        const uint2 inc2 = s4_lds64(edge1_s + kInc2 + (code[u] << 3));
-                        const float qx2 = __fsub_rn(xr[u], E2.x), qy2 = __fsub_rn(yr[u], E2.y);
-                        const float cr2 = __fmaf_rn(E2.z, qy2, -__fmul_rn(E2.w, qx2));
-                        if (cr2 >= 0.0f) { cam_lo += inc2.x; cam_hi += inc2.y; }
-                    }
-                }
-                if (__any_sync(0xffffffffu, rare)) {  // cold: cells crossed by three or more rays, or by both rays of one camera (next to a camera)
-                    uint32_t mm = 0;
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u) mm |= code[u] == kS4CodeMulti ? 1u << u : 0u;
-                    while (mm) {  // one of the lane's multi-edge points per trip
-                        const uint32_t us = (uint32_t)__ffs((int)mm) - 1u;
-                        mm &= mm - 1u;
-                        float px = xr[0], py = yr[0];
-#pragma unroll
-                        for (int u = 1; u < PPT; ++u)
-                            if (us == (uint32_t)u) { px = xr[u]; py = yr[u]; }
-                        // the class the point's code came from: its cull cell's outside the window, else its BEV cell's
-                        uint32_t cix, ciy;
-                        s4_bev_cell_xy<FASTDIV>(px, py, P.bev_range, two_r, rcp_two_r, resf, (uint32_t)res_m1, cix, ciy);
-                        const bool pp = max(cix - (uint32_t)win_lo, ciy - (uint32_t)win_lo) >= (uint32_t)win_w;
-                        const uint32_t cls = pp ? cullcls[(ciy >> L.cull_shift) * L.cull_dim + (cix >> L.cull_shift)] : class_of((int)cix, (int)ciy);
-                        uint32_t und = (cls >> 8) & 0xffffu, pass = 0xffffu;
-                        while (und) {
-                            const int e = __ffs((int)und) - 1;
-                            und &= und - 1u;
-                            const float4 E = s4_lds128(edge1_s + ((uint32_t)(e + 1) << 4));
-                            const float qx = __fsub_rn(px, E.x), qy = __fsub_rn(py, E.y);
-                            const float cr = __fmaf_rn(E.z, qy, -__fmul_rn(E.w, qx));
-                            if (!(cr >= 0.0f)) pass &= ~(1u << e);
-                        }
-                        // cameras with an undecided edge in this cell whose every undecided edge passed
-                        const uint32_t any_und = ((cls >> 8) | (cls >> 16)) & 0xffu;
-                        const uint32_t in = cls & any_und & pass & (pass >> 8);
-                        cam_lo += ((in & 0xfu) * 0x00204081u) & 0x01010101u;  // bit c -> byte c
-                        cam_hi += ((in >> 4) * 0x00204081u) & 0x01010101u;
-                    }
-                }
-            }
             // ---- phase D: points that have candidate boxes go to this warp's queue; whenever 32 are pending every lane tests
             // one of them (dense), instead of a handful of lanes looping while the rest of the warp idles.  The queue is drained at the top
             // of the next iteration (and here, half way, only if it could otherwise overflow).
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
+                uint32_t lt_mask;
+                asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+                if (FOV) {  // points of cells that a ray crosses (edge code != 0) go to the edge queue
+                    const bool edge = code[u] != 0u;
+                    const uint32_t me = __ballot_sync(0xffffffffu, edge);
+                    if (edge) {
+                        const uint32_t slot = (e_tail + __popc(me & lt_mask)) & (uint32_t)(kS4EdgeEntries - 1);
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(eq_s + (slot << 3)), "f"(xr[u]), "f"(yr[u]) : "memory");
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(eqc_s + slot), "r"(code[u]) : "memory");
+                    }
+                    e_tail += __popc(me);
+                    if (e_tail - e_head >= 32u) {
+                        __syncwarp();
+                        drain_edges(32u);
+                    }
+                }
                 const bool has = cand[u] != kCullEmpty;
                 const uint32_t m = __ballot_sync(0xffffffffu, has);
                 if (has) {
-                    uint32_t lt_mask;
-                    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
                     const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (uint32_t)(kS4QueueEntries - 1);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(queue_s + (slot << 4)), "f"(xr[u]), "f"(yr[u]), "f"(zr[u]),
                                  "f"(__uint_as_float(cand[u]))
@@ -687,22 +721,15 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     drain_queue(kDrain);
                 }
             }
-            if (FOV) {
-                pstate += PPT;
-                if (pstate > 255u - PPT) {  // spill the byte counters before any of them can wrap
-#pragma unroll
-                    for (int c = 0; c < MSC_MAX_CAMS; ++c) {
-                        const uint32_t v = ((c < 4 ? cam_lo : cam_hi) >> ((c & 3) * 8)) & 0xffu;
-                        if (v) s4_red_add(misc_s + (uint32_t)offsetof(S4Misc, stats) + (uint32_t)(5 + c) * 4u, v);
-                    }
-                    cam_lo = cam_hi = pstate = 0;
-                }
-            }
           }
         }
         while (q_tail != q_head) {
             __syncwarp();
             drain_queue(min(q_tail - q_head, kDrain));
+        }
+        if (FOV && e_tail != e_head) {  // (fewer than 32 are left)
+            __syncwarp();
+            drain_edges(e_tail - e_head);
         }
 
         // ------------------------------------------------------------ epilogue
