@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
         compute_wedge(P.image_w, A.in.lidar_calib + (size_t)sample * 7, A.in.cam_calib + ((size_t)sample * n_cams + c) * 7,
                       A.in.cam_K + ((size_t)sample * n_cams + c) * 9, wedges + ((size_t)sample * MSC_MAX_CAMS + c) * 6);
     }
-    // (4) stream4.cu's static partition: tile_off[s] = warp tiles (tile_pts rows of one sweep) of samples [0, s); the last block scans
-    if (tile_pts != 0u && blockIdx.x == gridDim.x - 1) {
+    // (4) stream4.cu's static partition: tile_off[s] = warp tiles (tile_pts rows of one sweep) of samples [0, s); the first block scans
+    // (it is scheduled first, so its serial passes over the sweep counts run beside the other blocks' projections, not after them)
+    if (tile_pts != 0u && blockIdx.x == 0) {
         __shared__ uint32_t part[256];
         uint32_t* const tile_off = reinterpret_cast<uint32_t*>(ws + T.tileoff_off);
         const int n = A.in.n_samples, tid = threadIdx.x;
@@ -143,14 +144,16 @@ __global__ void __launch_bounds__(256) fused_tables_kernel(const __grid_constant
 // share the cells of its bounding rectangle), into a workspace table the host pre-fills with kCullEmpty.
 __global__ void __launch_bounds__(128) fused_cullids_kernel(const __grid_constant__ FusedArgs A, const TableLayout T, unsigned char* __restrict__ ws) {
     const int sample = blockIdx.x, lane = threadIdx.x & 31;
-    const int b = (blockIdx.y * blockDim.x + threadIdx.x) >> 5;  // box of this warp inside its sample
     const int bx0 = A.in.sample_box_off[sample];
     int n_boxes = A.in.sample_box_off[sample + 1] - bx0;
     if (n_boxes > A.L.max_boxes) n_boxes = A.L.max_boxes;  // caller under-declared max_boxes_per_sample: the streaming kernel drops these boxes too
-    if (b >= n_boxes) return;
-    const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)(bx0 + b) * kBoxStride;
     uint32_t* ids = reinterpret_cast<uint32_t*>(ws + T.cullids_off) + (size_t)sample * (size_t)(A.L.cull_dim * A.L.cull_dim);
-    rasterise_box<1>(A, o, b, ids, lane, 32);
+    // the grid has a warp per DECLARED box; the loop covers samples that hold more (up to the room the streaming kernel has)
+    const int stride = (int)(gridDim.y * blockDim.x) >> 5;
+    for (int b = (int)(blockIdx.y * blockDim.x + threadIdx.x) >> 5; b < n_boxes; b += stride) {
+        const float* o = reinterpret_cast<const float*>(ws + T.boxprep_off) + (size_t)(bx0 + b) * kBoxStride;
+        rasterise_box<1>(A, o, b, ids, lane, 32);
+    }
 }
 
 
@@ -272,7 +275,7 @@ static int compute_layout(const msc_fused_ctx* X, const msc_params& P, int max_b
 // tables (prepared boxes, projection, wedges, housekeeping -> workspace), then the candidate-box ids of every cull cell; the per-cell
 // edge classes of the camera wedges are computed by the streaming kernels themselves, per sample, from the wedges
 static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLayout& T, unsigned char* ws, int n_boxes_total, int tile_pts,
-                         cudaStream_t stream) {
+                         int declared_max_boxes, cudaStream_t stream) {
     const int cams = args.P.n_cams > 0 ? args.P.n_cams : 1;
     long long work = (long long)n_boxes_total * cams;
     if ((long long)args.in.n_samples * cams > work) work = (long long)args.in.n_samples * cams;
@@ -282,7 +285,9 @@ static int launch_tables(msc_fused_ctx* X, const FusedArgs& args, const TableLay
     MSC_CUDA(cudaGetLastError());
     ++X->last_launches;
     if (n_boxes_total > 0 && args.L.max_boxes > 0) {
-        const dim3 cgrid((unsigned)args.in.n_samples, (unsigned)((args.L.max_boxes + 3) / 4));  // a warp per box, one grid column per sample
+        int per_sample = declared_max_boxes < args.L.max_boxes ? declared_max_boxes : args.L.max_boxes;
+        if (per_sample < 1) per_sample = 1;
+        const dim3 cgrid((unsigned)args.in.n_samples, (unsigned)((per_sample + 3) / 4));  // a warp per declared box, one grid column per sample
         fused_cullids_kernel<<<cgrid, 128, 0, stream>>>(args, T, ws);
         MSC_CUDA(cudaGetLastError());
         ++X->last_launches;
@@ -471,7 +476,7 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* X, const msc_params* para
     X->last_config = gen;
     X->last_window = args.L.win_w;
     X->last_smem = args.L.total_bytes;
-    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, gen == 10 ? 128 : 0, stream)) != MSC_OK) return rc;  // stream4.cu: 128-row warp tiles
+    if ((rc = launch_tables(X, args, T, ws, in->n_boxes, gen == 10 ? 128 : 0, in->max_boxes_per_sample, stream)) != MSC_OK) return rc;  // stream4.cu: 128-row warp tiles
     int grid;
     if (gen == 10) {
         // every CTA gets the same number of warp tiles; a batch of a few thousand rows is not spread thinner than one tile per warp
