@@ -29,6 +29,14 @@
 //     A.replica[]): the gather of a sharded batch without a collective.
 #include "fused_common.cuh"
 
+// Measured alternative, off: lanes of a candidate drain whose points lie in the same box find each other with __match_any_sync, reduce
+// count / nearest / sums with __reduce_*_sync over the group and one lane issues the box's five atomics.  Bit-identical, and 76 %
+// slower (2.86 vs 1.63 ms per 592 samples): MATCH.ANY plus, for masks that differ between lanes, ptxas's per-group loop of WARPSYNC +
+// REDUX cost far more than the same-address ATOMS they save (3 hits per box and drain on this workload).
+#ifndef MSC_S4_AGGREGATE
+#define MSC_S4_AGGREGATE 0
+#endif
+
 namespace msc {
 
 // Two launch shapes: PPT = 2 points per lane and pass (1024 threads x 64 registers, the default: more warps to hide latency) and PPT = 4
@@ -515,8 +523,35 @@ __global__ void __launch_bounds__(s4_threads(PPT), 1) stream4_kernel(const __gri
                     if (crowded1 && box_contains(boxp, b, e1.x, e1.y, e1.z)) { if (hit1 >= 0) accumulate(b, e1); else hit1 = b; }
                 }
             }
+#if MSC_S4_AGGREGATE
+            // lanes whose points lie in the same box reduce among themselves (count, nearest, three sums) and one of them updates the
+            // box's accumulators: the same integers, fewer same-address atomics
+            auto accumulate_grouped = [&](int hit, const float4& e) {
+                if (!__any_sync(0xffffffffu, hit >= 0)) return;
+                const uint32_t grp = __match_any_sync(0xffffffffu, hit);
+                const bool in = hit >= 0;
+                const float es2 = __fadd_rn(__fmul_rn(e.x, e.x), __fmul_rn(e.y, e.y));
+                const uint32_t fx = in ? (uint32_t)(__float2int_rn(__fmul_rn(e.x, A.cscale)) + A.centroid_bias) : 0u;
+                const uint32_t fy = in ? (uint32_t)(__float2int_rn(__fmul_rn(e.y, A.cscale)) + A.centroid_bias) : 0u;
+                const uint32_t fz = in ? (uint32_t)(__float2int_rn(__fmul_rn(e.z, A.cscale)) + A.centroid_bias) : 0u;
+                const uint32_t sx = __reduce_add_sync(grp, fx), sy = __reduce_add_sync(grp, fy), sz = __reduce_add_sync(grp, fz);  // < 2^30
+                const uint32_t mn = __reduce_min_sync(grp, __float_as_uint(es2));  // (es2 >= 0 or NaN-free: float order = unsigned order)
+                if (in && (uint32_t)lane == (uint32_t)__ffs((int)grp) - 1u) {
+                    const uint32_t acc_s = smem_s + (uint32_t)L.boxacc_off + (uint32_t)hit * (uint32_t)(kAccWords * 4);
+                    s4_red_add(acc_s, (uint32_t)__popc(grp));
+                    asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(acc_s + 4u), "r"(mn) : "memory");
+                    const uint32_t ox = s4_atom_add(acc_s + 8u, sx), oy = s4_atom_add(acc_s + 12u, sy), oz = s4_atom_add(acc_s + 16u, sz);
+                    if (ox > ~sx) s4_red_add(acc_s + 20u, 1u);
+                    if (oy > ~sy) s4_red_add(acc_s + 24u, 1u);
+                    if (oz > ~sz) s4_red_add(acc_s + 28u, 1u);
+                }
+            };
+            accumulate_grouped(hit0, e0);
+            if (kDrain == 64u) accumulate_grouped(hit1, e1);
+#else
             if (hit0 >= 0) accumulate(hit0, e0);
             if (hit1 >= 0) accumulate(hit1, e1);
+#endif
             q_head += n_take;
         };
         // ---- exact cross products for the points of cells that image-column rays cross, 32 queued points at a time (one per lane): the
