@@ -89,6 +89,23 @@ def test_fused_ragged_and_empty_inputs(engine):
     check_fused(engine, [c])                    # ... and one without a single point
 
 
+def test_fused_edge_queue_counter_spill(engine):
+    """stream4.cu keeps the exact wedge tests' per-camera counts in eight 8-bit counters per lane and spills them before the 255th
+    queue drain of a sample part.  A 30-sweep sample classified on 4 m cull cells (most cells are crossed by an image-column ray)
+    with a 16-cell window sends well over 255 x 32 points per warp through the edge queue."""
+    s = make_sample(47, n_sweeps=30, n_boxes=12)
+    try:
+        _capi.set_option("cull_shift", 3)
+        _capi.set_option("window", 16)
+        for ppt, grid in ((2, 1), (4, 3)):  # (few CTAs: ~590 / ~390 drains per warp and sample part)
+            _capi.set_option("ppt", ppt)
+            _capi.set_option("grid", grid)
+            check_fused(engine, [s], config=10)
+    finally:
+        for k, v in (("ppt", _capi.DEFAULT_FUSED_PPT), ("grid", 0), ("window", 0), ("cull_shift", -1), ("config", _capi.DEFAULT_FUSED_CONFIG)):
+            _capi.set_option(k, v)
+
+
 def test_fused_crowded_cell_and_max_boxes(engine):
     s = make_sample(40, n_sweeps=2, n_boxes=60)
     base = s["annotations"][0]
