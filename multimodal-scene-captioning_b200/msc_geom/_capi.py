@@ -13,7 +13,14 @@ ABI_VERSION = 2
 
 
 class MscError(RuntimeError):
-    pass
+    """A non-zero status of the C-ABI; `status` is the msc_status value (include/msc_geom.h)."""
+
+    def __init__(self, message: str, status: int = 0):
+        super().__init__(message)
+        self.status = status
+
+
+MSC_ERR_UNSUPPORTED = -3
 
 
 class MscParams(C.Structure):
@@ -126,7 +133,7 @@ DEFAULT_FUSED_PPT = 2       # stream4.cu launch shape: 2 points per lane (768 th
 def check(status: int, what: str):
     if status != 0:
         msg = load().msc_last_error().decode("utf-8", "replace")
-        raise MscError(f"{what} failed with status {status}: {msg}")
+        raise MscError(f"{what} failed with status {status}: {msg}", status)
 
 
 class FusedContext:

@@ -152,11 +152,14 @@ class NuScenesLoader:
         from PIL import Image
         if self.engine is not None:
             from . import ops
-            from ._capi import MscError
+            from ._capi import MSC_ERR_UNSUPPORTED, MscError
             try:
                 return ops.decode_jpeg_batch(self.engine, [np.fromfile(str(p), dtype=np.uint8) for p in paths])
-            except MscError:
-                pass  # a flavour the device decoder refuses: the reference's decoder handles the whole sample
+            except MscError as e:
+                # only a file flavour the decoder declares unsupported (progressive, 12-bit, CMYK ...: not nuScenes camera frames) goes
+                # to the reference's decoder; a missing library, a corrupt stream or a failed launch is an error, not a detour
+                if e.status != MSC_ERR_UNSUPPORTED:
+                    raise
         return [np.array(Image.open(p)) for p in paths]
 
     def scene_sample_tokens(self, scene_token: str) -> List[str]:

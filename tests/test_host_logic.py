@@ -195,3 +195,28 @@ def test_jpeg_header_parser_and_entropy_decoder_on_the_host():
 
 def _capi_status(name):
     return {"MSC_ERR_BAD_ARGUMENT": -1, "MSC_ERR_LAUNCH": -2, "MSC_ERR_UNSUPPORTED": -3, "MSC_ERR_NO_DEVICE": -4}[name]
+
+
+def test_loader_only_detours_to_pil_for_unsupported_jpeg_flavours(tmp_path, monkeypatch):
+    """NuScenesLoader._load_cameras with an engine: a file flavour the decoder reports as MSC_ERR_UNSUPPORTED goes to the reference's
+    decoder (PIL); any other failure of the CUDA path -- missing library, corrupt stream, failed launch -- is raised, never hidden."""
+    from PIL import Image
+    from msc_geom import _capi, ops
+    from msc_geom.nuscenes_loader import NuScenesLoader
+    img = np.random.default_rng(1).integers(0, 255, (24, 40, 3), dtype=np.uint8)
+    path = tmp_path / "cam.jpg"
+    Image.fromarray(img).save(path, "JPEG", quality=95)
+    loader = NuScenesLoader.__new__(NuScenesLoader)  # (no devkit tables needed for this method)
+    loader.engine = object()
+
+    def refuse(eng, blobs, **kw):
+        raise _capi.MscError("msc_jpeg_info failed with status -3: progressive", _capi.MSC_ERR_UNSUPPORTED)
+    monkeypatch.setattr(ops, "decode_jpeg_batch", refuse)
+    got = loader._load_cameras([path])
+    assert np.array_equal(got[0], np.array(Image.open(path)))
+    for status in (-1, -2, -4, 0):
+        def fail(eng, blobs, status=status, **kw):
+            raise _capi.MscError("failed", status)
+        monkeypatch.setattr(ops, "decode_jpeg_batch", fail)
+        with pytest.raises(_capi.MscError):
+            loader._load_cameras([path])
