@@ -220,3 +220,37 @@ def test_loader_only_detours_to_pil_for_unsupported_jpeg_flavours(tmp_path, monk
         monkeypatch.setattr(ops, "decode_jpeg_batch", fail)
         with pytest.raises(_capi.MscError):
             loader._load_cameras([path])
+
+
+def test_static_partition_arithmetic_matches_brute_force():
+    """The closed forms stream4.cu uses for its static partition of the batch's warp tiles over G CTAs (CTA c owns global tiles
+    [c * total // G, (c + 1) * total // G)): the owner of a tile, and the number of CTAs that own at least one tile of a sample --
+    the count the last-ticket finalisation waits for.  Restated here and checked against enumeration, including totals below G, where
+    most CTAs own nothing (the case a contiguous-owners formula gets wrong)."""
+    rng = np.random.default_rng(11)
+
+    def owner(r, total, G):  # stream4.cu: cta_of
+        return ((r + 1) * G + total - 1) // total - 1
+
+    def n_parts(off, n, total, G):  # stream4.cu: parts of the sample whose tiles are [off, off + n)
+        return owner(off + n - 1, total, G) - owner(off, total, G) + 1 if total >= G else n
+
+    for _ in range(300):
+        G = int(rng.integers(1, 200))
+        sizes = rng.integers(0, 40, int(rng.integers(1, 12)))
+        if rng.random() < 0.3:
+            sizes = rng.integers(0, 3000, len(sizes))
+        total = int(sizes.sum())
+        if total == 0:
+            continue
+        lo = [c * total // G for c in range(G)]
+        hi = [(c + 1) * total // G for c in range(G)]
+        own = np.empty(total, np.int64)
+        for c in range(G):
+            own[lo[c]:hi[c]] = c
+        assert all(owner(r, total, G) == own[r] for r in rng.integers(0, total, 50))
+        off = 0
+        for n in map(int, sizes):
+            if n:
+                assert n_parts(off, n, total, G) == len(set(own[off:off + n].tolist())), (G, total, off, n)
+            off += n
