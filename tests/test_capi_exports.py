@@ -56,3 +56,26 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in txt.lower() or f in ("synthetic.py",), f"{f} mentions the oracle"
+
+
+def test_streaming_kernel_sass_uses_tma_and_has_no_spills():
+    """Static evidence on the shipped library: the default instantiation of the streaming kernel moves its rows with the TMA unit
+    (UBLKCP completing on an mbarrier: SYNCS), accumulates with native shared-memory integer atomics and global reductions, runs the
+    f64 transform on DFMA -- and has no local-memory traffic (LDL / STL: register spills would show up there)."""
+    import shutil
+    import subprocess
+    import pytest
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    fun = "_ZN3msc14stream4_kernelILb1ELb1ELi2ELb1EEEvNS_9FusedArgsENS_11TableLayoutEPh"
+    out = subprocess.run([tool, "-sass", "-fun", fun, _capi.lib_path()], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "Function : " + fun in out.stdout, out.stderr[:300]
+    ops = set()
+    for line in out.stdout.splitlines():
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)", line)
+        if m:
+            ops.add(m.group(1))
+    for need in ("UBLKCP", "SYNCS", "ATOMS", "REDG", "DFMA", "F2F"):
+        assert any(o.startswith(need) for o in ops), f"{need} missing from the streaming kernel's SASS"
+    assert not any(o.startswith(("LDL", "STL")) for o in ops), "local-memory instructions (spills) in the streaming kernel"
