@@ -143,7 +143,7 @@ int msc_fused_evidence_batch_replicated(msc_fused_ctx* ctx, const msc_params* pa
                                         void* stream);
 
 /* Tunables of the fused kernel (for the benchmark sweep; defaults are chosen at build time).
- * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv", "cull_shift" (-1 auto),
+ * set: "fov" (0/1 per-camera wedge counting), "window" (BEV smem window width in cells, 0 = auto), "fastdiv", "cull_shift" (-1 auto: cull cells of at most 2 m, coarser if the grid would exceed 64 x 64 cells),
  * "config" (0 = auto, the default: stream4.cu; 10 / 7 force stream4.cu / fused_stream.cu; fov_keep_mask != 0 always takes
  * fused_stream.cu), "ppt" (stream4.cu launch shape: 2 = 1024 threads x 2 points per lane, 4 = 512 threads x 4), "grid" (CTAs of the
  * stream4.cu launch, 0 = auto), "time_kernel".  get: also "last_window", "last_smem", "last_fastdiv", "last_grid", "last_config",

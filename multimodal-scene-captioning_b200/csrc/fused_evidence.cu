@@ -216,7 +216,12 @@ static void cull_geometry(const msc_params& P, int opt_cull_shift, int* shift, i
     const float cell_m = 2.0f * P.bev_range / (float)P.bev_res;
     int sh = 0;
     if (opt_cull_shift >= 0) sh = opt_cull_shift;
-    else while ((float)(1 << (sh + 1)) * cell_m <= 2.0f + 1e-6f && sh < 10) ++sh;
+    else {
+        // auto: the largest power-of-two multiple of a BEV cell that is not above 2 m -- and coarser still until the cull grid has at
+        // most 64 x 64 cells (its id and count tables sit in shared memory: 32 KB; e.g. 0.512 m cells would give a 100 x 100 grid)
+        while ((float)(1 << (sh + 1)) * cell_m <= 2.0f + 1e-6f && sh < 10) ++sh;
+        while ((((P.bev_res - 1) >> sh) + 1) > 64 && sh < 10) ++sh;
+    }
     *shift = sh;
     *dim = ((P.bev_res - 1) >> sh) + 1;
 }

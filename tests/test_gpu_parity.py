@@ -189,6 +189,11 @@ def test_fused_other_grid_and_exact_division_path(engine):
     # a grid smaller than the fine edge-class table of the streaming kernel: the table then covers every cell, clipped edge cells included
     check_fused(engine, s, params=GeomParams(range_max=9.5, bev_range=10.0, bev_res=40))
     check_fused(engine, s, params=GeomParams(range_max=24.0, bev_range=16.0, bev_res=48))   # range beyond the grid: points clip into edge cells
+    # cell sizes just above a power-of-two fraction of 2 m (0.512 m, 0.256 m): the automatic cull grid is capped at 64 x 64 cells so that
+    # its tables fit beside 32 warp blocks (a 100 x 100 grid of 1.024 m cells would not)
+    check_fused(engine, s, params=GeomParams(range_max=50.0, bev_range=51.2, bev_res=200))
+    check_fused(engine, s, params=GeomParams(range_max=50.0, bev_range=51.2, bev_res=400))
+    check_fused(engine, s, params=GeomParams(range_max=50.0, bev_range=100.0, bev_res=400))
 
 
 def test_fused_many_sweeps_and_camera_counts(engine):
